@@ -1,0 +1,733 @@
+// engine.cu -- the C-ABI of include/q2w_b200.h: model upload, state/workspaces, and the forward pass
+// PCM -> log-mel -> conv stem -> 32 pre-LN blocks -> avg-pool(2) -> final LayerNorm, as a sequence of sm_100a kernels
+// on one stream.  This file replaces what src/qwen2-whisper.cpp did through ggml_backend_sched_* (graph build,
+// alloc, split, compute): there is no graph IR, no allocator and no backend dispatch -- workspaces are static per
+// micro-batch and the op order below IS the encoder (Appendix C of SURVEY.md; reference :1892-1952, :1954-2203).
+#include "../../include/q2w_b200.h"
+#include "ops.h"
+
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+using namespace q2w;
+
+namespace {
+
+thread_local char g_err[512] = "";
+std::atomic<long> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CK(call)                                                                                       \
+    do {                                                                                               \
+        cudaError_t e__ = (call);                                                                      \
+        if (e__ != cudaSuccess)                                                                        \
+            return fail(Q2W_E_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+    } while (0)
+
+// a kernel launch wrapper result: count it, then check
+#define CKL(call)                                                                                      \
+    do {                                                                                               \
+        g_launches.fetch_add(1, std::memory_order_relaxed);                                            \
+        CK(call);                                                                                      \
+    } while (0)
+
+int64_t now_us() {
+    return std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+size_t type_row_bytes(int type, int64_t ne0) {
+    switch (type) {
+        case Q2W_TYPE_F32: return static_cast<size_t>(ne0) * 4;
+        case Q2W_TYPE_F16: return static_cast<size_t>(ne0) * 2;
+        case Q2W_TYPE_Q8_0: return static_cast<size_t>(ne0 / 32) * 34;   // block_q8_0 ggml-common.h:186-191
+        case Q2W_TYPE_Q4_0: return static_cast<size_t>(ne0 / 32) * 18;   // block_q4_0 ggml-common.h:144-148
+        default: return 0;
+    }
+}
+
+struct Tensor {
+    void* d = nullptr;        // device storage (type dev_type)
+    int file_type = 0;        // ggml type the model file must carry
+    int dev_type = 0;         // type kept on the device (F32 matrices/conv kernels are converted to F16 once)
+    int n_dims = 1;
+    int64_t ne[3] = {1, 1, 1};
+    bool loaded = false;
+    bool owns = true;
+    int64_t nelements() const { return ne[0] * ne[1] * ne[2]; }
+    int64_t nrows() const { return ne[1] * ne[2]; }
+    size_t file_bytes() const { return type_row_bytes(file_type, ne[0]) * static_cast<size_t>(nrows()); }
+    size_t dev_bytes() const { return type_row_bytes(dev_type, ne[0]) * static_cast<size_t>(nrows()); }
+};
+
+struct Layer {
+    Tensor ln1_w, ln1_b, q_w, q_b, k_w, v_w, v_b, o_w, o_b, ln2_w, ln2_b, fc1_w, fc1_b, fc2_w, fc2_b;
+    void* qkv_w = nullptr;    // q_w | k_w | v_w rows, contiguous (ggml row layout keeps blocks row-local)
+    float* qkv_b = nullptr;   // q_b | 0 | v_b
+};
+
+}  // namespace
+
+struct q2w_model {
+    q2w_hparams hp{};
+    int wtype = Q2W_TYPE_F16;      // file type of the 2-D matrices
+    int wtype_dev = Q2W_TYPE_F16;  // what the GEMM path sees (F16 / Q8_0 / Q4_0)
+    int device = 0;
+    Tensor pe, conv1_w, conv1_b, conv2_w, conv2_b, ln_w, ln_b;
+    std::vector<Layer> layers;
+    std::map<std::string, Tensor*> by_name;
+    MelPlan* mel = nullptr;
+    int n_loaded = 0;
+    bool finalized = false;
+    size_t weight_bytes = 0;
+    cudaStream_t stream = nullptr;
+};
+
+struct q2w_state {
+    q2w_model* m = nullptr;
+    int max_batch = 1;
+    cudaStream_t stream = nullptr;
+    // dims
+    int T = 0, T2 = 0, D = 0, H = 0, FF = 0, n_mel = 0, win_samples = 0, ld_mel = 0, n_frames_batch = 0;
+    // workspaces (sized for max_batch windows)
+    float* x = nullptr;        // residual stream f32 [B*T, D]
+    __half* ln = nullptr;      // LayerNorm out f16 [B*T, D]
+    __half* qkv = nullptr;     // [B*T, 3D]        (aliases conv2 operand A2)
+    __half* att = nullptr;     // [B*T, D]         (aliases conv1 operand A1)
+    __half* h = nullptr;       // [B*T, 4D]        (aliases conv1 output h1 [B*T2, D])
+    __half* wscratch = nullptr;  // decoded weight matrix (largest: 4D*D)
+    float* pcm_dev = nullptr;  // [B, win_samples]
+    int* nsamp_dev = nullptr;  // [B]
+    float* logmel = nullptr;   // [B, n_mel, ld_mel]
+    float* winmax = nullptr;   // [B] ordered int keys
+    // results
+    float* emb = nullptr;      // [n_windows, T/2, D]
+    size_t emb_cap_windows = 0;
+    int emb_windows = 0;
+    // API mel (whisper_pcm_to_mel / whisper_set_mel)
+    float* api_mel = nullptr;
+    size_t api_mel_cap = 0;
+    int api_n_len = 0, api_n_len_org = 0, api_ld = 0;
+    float* api_pcm = nullptr;
+    size_t api_pcm_cap = 0;
+    float* api_max = nullptr;
+    // timers
+    int64_t t_mel_us = 0, t_encode_us = 0;
+    int32_t n_encode = 0;
+};
+
+namespace {
+
+int alloc_tensor(Tensor& t, int file_type, int dev_type, int n_dims, int64_t ne0, int64_t ne1, int64_t ne2) {
+    t.file_type = file_type;
+    t.dev_type = dev_type;
+    t.n_dims = n_dims;
+    t.ne[0] = ne0; t.ne[1] = ne1; t.ne[2] = ne2;
+    if (t.owns) CK(cudaMalloc(&t.d, t.dev_bytes()));
+    return Q2W_OK;
+}
+
+void free_tensor(Tensor& t) {
+    if (t.owns && t.d) cudaFree(t.d);
+    t.d = nullptr;
+}
+
+int check_device(int device) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(Q2W_E_NO_DEVICE, "no CUDA device visible: libq2w_b200 has no CPU fallback");
+    }
+    if (device < 0 || device >= n) return fail(Q2W_E_INVALID, "device ordinal %d out of range (0..%d)", device, n - 1);
+    cudaDeviceProp p;
+    CK(cudaGetDeviceProperties(&p, device));
+    if (p.major != 10) return fail(Q2W_E_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", device, p.major, p.minor);
+    return Q2W_OK;
+}
+
+// y = A x W^T with W in the model's device type: quantised matrices are decoded to f16 into the (L2-resident) scratch first
+int weight_gemm(q2w_state* s, const __half* A, int lda, const void* W, int wtype_dev, int M, int N, int K, const float* bias,
+                void* out, int ldo, GemmEpilogue epi, const float* resid, const float* pos, int pos_period, int scale_cols,
+                float scale) {
+    const __half* Wh = static_cast<const __half*>(W);
+    if (wtype_dev != Q2W_TYPE_F16) {
+        CKL(dequant_to_f16(W, wtype_dev, s->wscratch, static_cast<size_t>(N), K, s->stream));
+        Wh = s->wscratch;
+    }
+    GemmArgs g{};
+    g.A = A; g.lda = lda; g.W = Wh; g.ldw = K; g.M = M; g.N = N; g.K = K; g.bias = bias; g.out = out; g.ldo = ldo;
+    g.resid = resid; g.pos = pos; g.pos_period = pos_period; g.scale_cols = scale_cols; g.scale = scale;
+    CKL(gemm_f16_tcgen05(g, epi, s->stream));
+    return Q2W_OK;
+}
+
+// conv stem + encoder for Bm windows whose conv1 operand A1 (in s->att) is ready; writes emb rows [w0, w0+Bm)
+int forward_from_a1(q2w_state* s, int Bm, int w0) {
+    q2w_model* m = s->m;
+    const int T = s->T, T2 = s->T2, D = s->D, H = s->H, FF = s->FF;
+    const int M = Bm * T;
+    const float eps = 1e-5f;  // hparams.eps, src/qwen2-whisper.cpp:579
+    __half* A1 = s->att;
+    __half* h1 = s->h;
+    __half* A2 = s->qkv;
+    int rc;
+    // conv1 (k3 s1 p1) + bias + GELU   (:1922-1925)
+    if ((rc = weight_gemm(s, A1, 3 * s->n_mel, m->conv1_w.d, Q2W_TYPE_F16, Bm * T2, D, 3 * s->n_mel,
+                          static_cast<const float*>(m->conv1_b.d), h1, D, EPI_BIAS_GELU_F16, nullptr, nullptr, 0, 0, 1.f)))
+        return rc;
+    // conv2 (k3 s2 p1) + bias + GELU, transposed to time-major and + positional embedding   (:1927-1930, :2001-2005)
+    CKL(conv2_im2col(h1, A2, Bm, T2, D, s->stream));
+    if ((rc = weight_gemm(s, A2, 3 * D, m->conv2_w.d, Q2W_TYPE_F16, M, D, 3 * D, static_cast<const float*>(m->conv2_b.d),
+                          s->x, D, EPI_BIAS_GELU_POS_F32, nullptr, static_cast<const float*>(m->pe.d), T, 0, 1.f)))
+        return rc;
+    const float kq_scale = 1.0f / sqrtf(static_cast<float>(D / H));  // :1985
+    for (int il = 0; il < m->hp.n_audio_layer; ++il) {
+        Layer& L = m->layers[il];
+        // pre-LN + fused QKV projection (+bias, Q * KQscale)   (:2019-2055)
+        CKL(layernorm_f32_to_f16(s->x, static_cast<const float*>(L.ln1_w.d), static_cast<const float*>(L.ln1_b.d), s->ln, M, D,
+                                 eps, s->stream));
+        if ((rc = weight_gemm(s, s->ln, D, L.qkv_w, m->wtype_dev, M, 3 * D, D, L.qkv_b, s->qkv, 3 * D, EPI_BIAS_F16, nullptr,
+                              nullptr, 0, D, kq_scale)))
+            return rc;
+        // softmax(Q K^T) V per head   (:2080-2106)
+        CKL(attention_f16(s->qkv, s->att, Bm, T, H, s->stream));
+        // out-proj + bias + residual   (:2112-2120)
+        if ((rc = weight_gemm(s, s->att, D, L.o_w.d, m->wtype_dev, M, D, D, static_cast<const float*>(L.o_b.d), s->x, D,
+                              EPI_BIAS_RESID_F32, s->x, nullptr, 0, 0, 1.f)))
+            return rc;
+        // MLP: LN, fc1 + GELU, fc2 + residual   (:2128-2154)
+        CKL(layernorm_f32_to_f16(s->x, static_cast<const float*>(L.ln2_w.d), static_cast<const float*>(L.ln2_b.d), s->ln, M, D,
+                                 eps, s->stream));
+        if ((rc = weight_gemm(s, s->ln, D, L.fc1_w.d, m->wtype_dev, M, FF, D, static_cast<const float*>(L.fc1_b.d), s->h, FF,
+                              EPI_BIAS_GELU_F16, nullptr, nullptr, 0, 0, 1.f)))
+            return rc;
+        if ((rc = weight_gemm(s, s->h, FF, L.fc2_w.d, m->wtype_dev, M, D, FF, static_cast<const float*>(L.fc2_b.d), s->x, D,
+                              EPI_BIAS_RESID_F32, s->x, nullptr, 0, 0, 1.f)))
+            return rc;
+    }
+    // avg-pool(2,2) over time + final LayerNorm   (:2160-2181)
+    float* out = s->emb + static_cast<size_t>(w0) * (T / 2) * D;
+    CKL(pool2_layernorm_f32(s->x, static_cast<const float*>(m->ln_w.d), static_cast<const float*>(m->ln_b.d), out, Bm, T, D, eps,
+                            s->stream));
+    return Q2W_OK;
+}
+
+int ensure_emb(q2w_state* s, int n_windows) {
+    if (static_cast<size_t>(n_windows) > s->emb_cap_windows) {
+        if (s->emb) cudaFree(s->emb);
+        s->emb = nullptr;
+        s->emb_cap_windows = 0;
+        CK(cudaMalloc(&s->emb, static_cast<size_t>(n_windows) * (s->T / 2) * s->D * sizeof(float)));
+        s->emb_cap_windows = n_windows;
+    }
+    return Q2W_OK;
+}
+
+// mel + conv1 operand for Bm windows resident in s->pcm_dev, then the encoder
+int batch_chunk(q2w_state* s, const float* pcm_dev, size_t stride, int Bm, int w0) {
+    CKL(mel_logpower(s->m->mel, pcm_dev, stride, s->nsamp_dev, s->win_samples, Bm, s->n_frames_batch, s->logmel, s->ld_mel,
+                     s->winmax, s->stream));
+    g_launches.fetch_add(1);  // mel_logpower issues two kernels (key init + main)
+    CKL(mel_to_conv1_operand(s->logmel, s->ld_mel, s->n_frames_batch, s->n_mel, s->winmax, 1, 0, s->T2, Bm, s->att, s->stream));
+    return forward_from_a1(s, Bm, w0);
+}
+
+}  // namespace
+
+// =============================================================================================== model
+extern "C" {
+
+int q2w_model_create(q2w_model** out, const q2w_hparams* hp, int wtype, int device) {
+    if (!out || !hp) return fail(Q2W_E_INVALID, "null argument");
+    *out = nullptr;
+    int rc = check_device(device);
+    if (rc) return rc;
+    if (wtype != Q2W_TYPE_F32 && wtype != Q2W_TYPE_F16 && wtype != Q2W_TYPE_Q8_0 && wtype != Q2W_TYPE_Q4_0)
+        return fail(Q2W_E_UNSUPPORTED, "weight type %d not on this path (F32/F16/Q8_0/Q4_0 only)", wtype);
+    const int D = hp->n_audio_state, H = hp->n_audio_head, L = hp->n_audio_layer, T = hp->n_audio_ctx, NM = hp->n_mels;
+    if (D <= 0 || H <= 0 || L <= 0 || T <= 0 || NM <= 0) return fail(Q2W_E_INVALID, "bad hparams");
+    if (D % H || D / H != 64) return fail(Q2W_E_UNSUPPORTED, "head_dim %d unsupported (attention kernel is specialised for 64)", H ? D / H : 0);
+    if (D % 32 || D > 1280 || (T & 1) || (3 * NM) % 8)
+        return fail(Q2W_E_UNSUPPORTED, "hparams outside the supported envelope (n_audio_state %% 32, <= 1280; even n_audio_ctx)");
+    CK(cudaSetDevice(device));
+    q2w_model* m = new q2w_model();
+    m->hp = *hp;
+    m->wtype = wtype;
+    m->wtype_dev = (wtype == Q2W_TYPE_F32) ? Q2W_TYPE_F16 : wtype;
+    m->device = device;
+    m->layers.resize(L);
+    const int vtype = (wtype == Q2W_TYPE_F32) ? Q2W_TYPE_F32 : Q2W_TYPE_F16;  // conv kernel type, :1543
+    const int FF = 4 * D;
+#define ALLOC(t, ft, dt, nd, a, b, c) do { if ((rc = alloc_tensor(t, ft, dt, nd, a, b, c))) { q2w_model_free(m); return rc; } } while (0)
+    if (cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking) != cudaSuccess) { q2w_model_free(m); return fail(Q2W_E_CUDA, "stream create failed"); }
+    // shapes in ggml order (innermost first), :1591-1638
+    ALLOC(m->pe, Q2W_TYPE_F32, Q2W_TYPE_F32, 2, D, T, 1);
+    ALLOC(m->conv1_w, vtype, Q2W_TYPE_F16, 3, 3, NM, D);
+    ALLOC(m->conv1_b, Q2W_TYPE_F32, Q2W_TYPE_F32, 2, 1, D, 1);
+    ALLOC(m->conv2_w, vtype, Q2W_TYPE_F16, 3, 3, D, D);
+    ALLOC(m->conv2_b, Q2W_TYPE_F32, Q2W_TYPE_F32, 2, 1, D, 1);
+    ALLOC(m->ln_w, Q2W_TYPE_F32, Q2W_TYPE_F32, 1, D, 1, 1);
+    ALLOC(m->ln_b, Q2W_TYPE_F32, Q2W_TYPE_F32, 1, D, 1, 1);
+    m->by_name["embed_positions.weight"] = &m->pe;
+    m->by_name["conv1.weight"] = &m->conv1_w;
+    m->by_name["conv1.bias"] = &m->conv1_b;
+    m->by_name["conv2.weight"] = &m->conv2_w;
+    m->by_name["conv2.bias"] = &m->conv2_b;
+    m->by_name["layer_norm.weight"] = &m->ln_w;
+    m->by_name["layer_norm.bias"] = &m->ln_b;
+    const size_t wrow = type_row_bytes(m->wtype_dev, D);
+    for (int i = 0; i < L; ++i) {
+        Layer& ly = m->layers[i];
+        if (cudaMalloc(&ly.qkv_w, wrow * 3 * D) != cudaSuccess || cudaMalloc(&ly.qkv_b, sizeof(float) * 3 * D) != cudaSuccess) {
+            q2w_model_free(m);
+            return fail(Q2W_E_NOMEM, "cudaMalloc failed for layer %d", i);
+        }
+        cudaMemsetAsync(ly.qkv_b, 0, sizeof(float) * 3 * D, m->stream);
+        ly.q_w.owns = ly.k_w.owns = ly.v_w.owns = false;
+        ly.q_b.owns = ly.v_b.owns = false;
+        ly.q_w.d = ly.qkv_w;
+        ly.k_w.d = static_cast<uint8_t*>(ly.qkv_w) + wrow * D;
+        ly.v_w.d = static_cast<uint8_t*>(ly.qkv_w) + wrow * 2 * D;
+        ly.q_b.d = ly.qkv_b;
+        ly.v_b.d = ly.qkv_b + 2 * D;
+        ALLOC(ly.ln1_w, Q2W_TYPE_F32, Q2W_TYPE_F32, 1, D, 1, 1);
+        ALLOC(ly.ln1_b, Q2W_TYPE_F32, Q2W_TYPE_F32, 1, D, 1, 1);
+        ALLOC(ly.q_w, wtype, m->wtype_dev, 2, D, D, 1);
+        ALLOC(ly.q_b, Q2W_TYPE_F32, Q2W_TYPE_F32, 1, D, 1, 1);
+        ALLOC(ly.k_w, wtype, m->wtype_dev, 2, D, D, 1);
+        ALLOC(ly.v_w, wtype, m->wtype_dev, 2, D, D, 1);
+        ALLOC(ly.v_b, Q2W_TYPE_F32, Q2W_TYPE_F32, 1, D, 1, 1);
+        ALLOC(ly.o_w, wtype, m->wtype_dev, 2, D, D, 1);
+        ALLOC(ly.o_b, Q2W_TYPE_F32, Q2W_TYPE_F32, 1, D, 1, 1);
+        ALLOC(ly.ln2_w, Q2W_TYPE_F32, Q2W_TYPE_F32, 1, D, 1, 1);
+        ALLOC(ly.ln2_b, Q2W_TYPE_F32, Q2W_TYPE_F32, 1, D, 1, 1);
+        ALLOC(ly.fc1_w, wtype, m->wtype_dev, 2, D, FF, 1);
+        ALLOC(ly.fc1_b, Q2W_TYPE_F32, Q2W_TYPE_F32, 1, FF, 1, 1);
+        ALLOC(ly.fc2_w, wtype, m->wtype_dev, 2, FF, D, 1);
+        ALLOC(ly.fc2_b, Q2W_TYPE_F32, Q2W_TYPE_F32, 1, D, 1, 1);
+        const std::string p = "layers." + std::to_string(i) + ".";
+        m->by_name[p + "self_attn_layer_norm.weight"] = &ly.ln1_w;
+        m->by_name[p + "self_attn_layer_norm.bias"] = &ly.ln1_b;
+        m->by_name[p + "self_attn.q_proj.weight"] = &ly.q_w;
+        m->by_name[p + "self_attn.q_proj.bias"] = &ly.q_b;
+        m->by_name[p + "self_attn.k_proj.weight"] = &ly.k_w;
+        m->by_name[p + "self_attn.v_proj.weight"] = &ly.v_w;
+        m->by_name[p + "self_attn.v_proj.bias"] = &ly.v_b;
+        m->by_name[p + "self_attn.out_proj.weight"] = &ly.o_w;
+        m->by_name[p + "self_attn.out_proj.bias"] = &ly.o_b;
+        m->by_name[p + "final_layer_norm.weight"] = &ly.ln2_w;
+        m->by_name[p + "final_layer_norm.bias"] = &ly.ln2_b;
+        m->by_name[p + "fc1.weight"] = &ly.fc1_w;
+        m->by_name[p + "fc1.bias"] = &ly.fc1_b;
+        m->by_name[p + "fc2.weight"] = &ly.fc2_w;
+        m->by_name[p + "fc2.bias"] = &ly.fc2_b;
+    }
+#undef ALLOC
+    for (auto& kv : m->by_name) m->weight_bytes += kv.second->dev_bytes();
+    *out = m;
+    return Q2W_OK;
+}
+
+int q2w_model_upload_filters(q2w_model* m, const float* filters, int n_mel, int n_fft) {
+    if (!m || !filters) return fail(Q2W_E_INVALID, "null argument");
+    if (n_mel != m->hp.n_mels) return fail(Q2W_E_BAD_SHAPE, "filterbank has %d mel bands, model expects %d", n_mel, m->hp.n_mels);
+    if (n_fft != 201) return fail(Q2W_E_BAD_SHAPE, "filterbank has %d bins, expected 1 + WHISPER_N_FFT/2 = 201", n_fft);
+    CK(cudaSetDevice(m->device));
+    if (m->mel) { mel_plan_destroy(m->mel); m->mel = nullptr; }
+    CK(mel_plan_create(&m->mel, filters, n_mel, n_fft, m->stream));
+    return Q2W_OK;
+}
+
+int q2w_model_upload_tensor(q2w_model* m, const char* name, int ggml_type, int n_dims, const int32_t* ne, const void* data,
+                            size_t nbytes) {
+    if (!m || !name || !ne || !data) return fail(Q2W_E_INVALID, "null argument");
+    auto it = m->by_name.find(name);
+    if (it == m->by_name.end()) return fail(Q2W_E_UNKNOWN_TENSOR, "unknown tensor '%s' in model file", name);
+    Tensor& t = *it->second;
+    int64_t got[3] = {1, 1, 1};
+    int64_t nel = 1;
+    if (n_dims < 1 || n_dims > 3) return fail(Q2W_E_BAD_SHAPE, "tensor '%s': n_dims %d", name, n_dims);
+    for (int i = 0; i < n_dims; ++i) { got[i] = ne[i]; nel *= ne[i]; }
+    if (nel != t.nelements()) return fail(Q2W_E_BAD_SHAPE, "tensor '%s' has wrong size in model file", name);
+    if (got[0] != t.ne[0] || got[1] != t.ne[1] || got[2] != t.ne[2])
+        return fail(Q2W_E_BAD_SHAPE, "tensor '%s' has wrong shape in model file: got [%lld, %lld, %lld], expected [%lld, %lld, %lld]", name,
+                    (long long) got[0], (long long) got[1], (long long) got[2], (long long) t.ne[0], (long long) t.ne[1], (long long) t.ne[2]);
+    if (ggml_type != t.file_type || nbytes != t.file_bytes())
+        return fail(Q2W_E_BAD_SIZE, "tensor '%s' has wrong size in model file: got type %d / %zu bytes, expected type %d / %zu bytes", name,
+                    ggml_type, nbytes, t.file_type, t.file_bytes());
+    CK(cudaSetDevice(m->device));
+    if (t.file_type == t.dev_type) {
+        CK(cudaMemcpyAsync(t.d, data, nbytes, cudaMemcpyHostToDevice, m->stream));
+        CK(cudaStreamSynchronize(m->stream));
+    } else {
+        // F32 matrix / conv kernel in an F32 model file: round to F16 once (the tensor-core operand type)
+        void* tmp = nullptr;
+        CK(cudaMalloc(&tmp, nbytes));
+        cudaError_t e = cudaMemcpyAsync(tmp, data, nbytes, cudaMemcpyHostToDevice, m->stream);
+        if (e == cudaSuccess) e = dequant_to_f16(tmp, Q2W_TYPE_F32, static_cast<__half*>(t.d), static_cast<size_t>(t.nrows()), static_cast<int>(t.ne[0]) , m->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(m->stream);
+        cudaFree(tmp);
+        if (e != cudaSuccess) return fail(Q2W_E_CUDA, "upload of '%s' failed: %s", name, cudaGetErrorString(e));
+    }
+    if (!t.loaded) { t.loaded = true; m->n_loaded++; }
+    return Q2W_OK;
+}
+
+int q2w_model_finalize(q2w_model* m) {
+    if (!m) return fail(Q2W_E_INVALID, "null argument");
+    if (m->n_loaded != static_cast<int>(m->by_name.size()))
+        return fail(Q2W_E_INCOMPLETE, "not all tensors loaded from model file - expected %zu, got %d", m->by_name.size(), m->n_loaded);
+    if (!m->mel) return fail(Q2W_E_INCOMPLETE, "mel filterbank not uploaded");
+    CK(cudaSetDevice(m->device));
+    CK(cudaStreamSynchronize(m->stream));
+    m->finalized = true;
+    return Q2W_OK;
+}
+
+void q2w_model_free(q2w_model* m) {
+    if (!m) return;
+    cudaSetDevice(m->device);
+    for (auto& kv : m->by_name) free_tensor(*kv.second);
+    for (auto& ly : m->layers) {
+        if (ly.qkv_w) cudaFree(ly.qkv_w);
+        if (ly.qkv_b) cudaFree(ly.qkv_b);
+    }
+    // tensors not yet registered by name (creation failed midway)
+    free_tensor(m->pe); free_tensor(m->conv1_w); free_tensor(m->conv1_b); free_tensor(m->conv2_w); free_tensor(m->conv2_b);
+    free_tensor(m->ln_w); free_tensor(m->ln_b);
+    if (m->mel) mel_plan_destroy(m->mel);
+    if (m->stream) cudaStreamDestroy(m->stream);
+    delete m;
+}
+
+int q2w_model_n_tensors_expected(const q2w_model* m) { return m ? static_cast<int>(m->by_name.size()) : 0; }
+int q2w_model_n_tensors_loaded(const q2w_model* m) { return m ? m->n_loaded : 0; }
+size_t q2w_model_weight_bytes(const q2w_model* m) { return m ? m->weight_bytes : 0; }
+
+// =============================================================================================== state
+int q2w_state_create(q2w_state** out, q2w_model* m, int max_batch) {
+    if (!out || !m) return fail(Q2W_E_INVALID, "null argument");
+    *out = nullptr;
+    if (!m->finalized) return fail(Q2W_E_INCOMPLETE, "model not finalized");
+    if (max_batch < 1) return fail(Q2W_E_INVALID, "max_batch must be >= 1");
+    CK(cudaSetDevice(m->device));
+    q2w_state* s = new q2w_state();
+    s->m = m;
+    s->max_batch = max_batch;
+    s->T = m->hp.n_audio_ctx; s->T2 = 2 * s->T; s->D = m->hp.n_audio_state; s->H = m->hp.n_audio_head; s->FF = 4 * s->D;
+    s->n_mel = m->hp.n_mels;
+    s->win_samples = s->T2 * 160;
+    s->n_frames_batch = s->T2 + 2;                      // frames T2, T2+1 still see real samples and enter the max (:2522, :2634)
+    s->ld_mel = (s->n_frames_batch + 15) / 16 * 16;
+    const size_t B = max_batch, T = s->T, D = s->D;
+    const size_t att_elems = std::max(T * D, static_cast<size_t>(s->T2) * 3 * s->n_mel);
+    const size_t wmax = std::max<size_t>(static_cast<size_t>(4) * D * D, 3 * D * D);
+    cudaError_t e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
+#define SALLOC(ptr, bytes) if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&(ptr)), (bytes))
+    SALLOC(s->x, B * T * D * sizeof(float));
+    SALLOC(s->ln, B * T * D * sizeof(__half));
+    SALLOC(s->qkv, B * T * 3 * D * sizeof(__half));
+    SALLOC(s->att, B * att_elems * sizeof(__half));
+    SALLOC(s->h, B * T * 4 * D * sizeof(__half));
+    SALLOC(s->wscratch, wmax * sizeof(__half));
+    SALLOC(s->pcm_dev, B * s->win_samples * sizeof(float));
+    SALLOC(s->nsamp_dev, B * sizeof(int));
+    SALLOC(s->logmel, B * s->n_mel * s->ld_mel * sizeof(float));
+    SALLOC(s->winmax, B * sizeof(float));
+    SALLOC(s->api_max, sizeof(float));
+#undef SALLOC
+    if (e != cudaSuccess) {
+        q2w_state_free(s);
+        return fail(e == cudaErrorMemoryAllocation ? Q2W_E_NOMEM : Q2W_E_CUDA, "state allocation failed: %s", cudaGetErrorString(e));
+    }
+    *out = s;
+    return Q2W_OK;
+}
+
+void q2w_state_free(q2w_state* s) {
+    if (!s) return;
+    cudaSetDevice(s->m->device);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    void* ptrs[] = {s->x, s->ln, s->qkv, s->att, s->h, s->wscratch, s->pcm_dev, s->nsamp_dev, s->logmel, s->winmax,
+                    s->emb, s->api_mel, s->api_pcm, s->api_max};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+}
+
+int q2w_pcm_to_mel(q2w_state* s, const float* pcm_host, int n_samples) {
+    if (!s || !pcm_host || n_samples <= 0) return fail(Q2W_E_INVALID, "bad argument");
+    CK(cudaSetDevice(s->m->device));
+    const int64_t t0 = now_us();
+    // n_len = (n + 30 s + 2*200 - 400) / 160 ; n_len_org = 1 + (n + 200 - 400) / 160   (:2594-2613)
+    const int n_len = static_cast<int>((static_cast<int64_t>(n_samples) + 480000) / 160);
+    const int n_len_org = 1 + (n_samples + 200 - 400) / 160;
+    const int ld = (n_len + 3) / 4 * 4;
+    const size_t need = static_cast<size_t>(s->n_mel) * ld;
+    if (need > s->api_mel_cap) {
+        if (s->api_mel) cudaFree(s->api_mel);
+        s->api_mel = nullptr; s->api_mel_cap = 0;
+        CK(cudaMalloc(&s->api_mel, need * sizeof(float)));
+        s->api_mel_cap = need;
+    }
+    if (static_cast<size_t>(n_samples) > s->api_pcm_cap) {
+        if (s->api_pcm) cudaFree(s->api_pcm);
+        s->api_pcm = nullptr; s->api_pcm_cap = 0;
+        CK(cudaMalloc(&s->api_pcm, static_cast<size_t>(n_samples) * sizeof(float)));
+        s->api_pcm_cap = n_samples;
+    }
+    CK(cudaMemcpyAsync(s->api_pcm, pcm_host, static_cast<size_t>(n_samples) * sizeof(float), cudaMemcpyHostToDevice, s->stream));
+    CKL(mel_logpower(s->m->mel, s->api_pcm, 0, nullptr, n_samples, 1, n_len, s->api_mel, ld, s->api_max, s->stream));
+    g_launches.fetch_add(1);
+    CKL(mel_normalize(s->api_mel, ld, n_len, s->n_mel, s->api_max, 1, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    s->api_n_len = n_len; s->api_n_len_org = n_len_org; s->api_ld = ld;
+    s->t_mel_us += now_us() - t0;
+    return Q2W_OK;
+}
+
+int q2w_set_mel(q2w_state* s, const float* mel_host, int n_len, int n_mel) {
+    if (!s || !mel_host || n_len <= 0) return fail(Q2W_E_INVALID, "bad argument");
+    if (n_mel != s->n_mel) return fail(Q2W_E_INVALID, "invalid number of mel bands: %d (expected %d)", n_mel, s->n_mel);
+    CK(cudaSetDevice(s->m->device));
+    const size_t need = static_cast<size_t>(n_mel) * n_len;
+    if (need > s->api_mel_cap) {
+        if (s->api_mel) cudaFree(s->api_mel);
+        s->api_mel = nullptr; s->api_mel_cap = 0;
+        CK(cudaMalloc(&s->api_mel, need * sizeof(float)));
+        s->api_mel_cap = need;
+    }
+    CK(cudaMemcpyAsync(s->api_mel, mel_host, need * sizeof(float), cudaMemcpyHostToDevice, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    s->api_n_len = n_len; s->api_n_len_org = n_len; s->api_ld = n_len;
+    return Q2W_OK;
+}
+
+int q2w_mel_n_len(const q2w_state* s) { return s ? s->api_n_len : 0; }
+int q2w_mel_n_len_org(const q2w_state* s) { return s ? s->api_n_len_org : 0; }
+
+int q2w_get_mel(q2w_state* s, float* out_host, size_t n_floats) {
+    if (!s || !out_host) return fail(Q2W_E_INVALID, "null argument");
+    if (!s->api_mel || s->api_n_len <= 0) return fail(Q2W_E_INVALID, "no mel in this state");
+    if (n_floats < static_cast<size_t>(s->n_mel) * s->api_n_len) return fail(Q2W_E_INVALID, "output buffer too small");
+    CK(cudaSetDevice(s->m->device));
+    CK(cudaMemcpy2DAsync(out_host, static_cast<size_t>(s->api_n_len) * sizeof(float), s->api_mel, static_cast<size_t>(s->api_ld) * sizeof(float),
+                         static_cast<size_t>(s->api_n_len) * sizeof(float), s->n_mel, cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    return Q2W_OK;
+}
+
+int q2w_encode(q2w_state* s, int mel_offset) {
+    if (!s) return fail(Q2W_E_INVALID, "null argument");
+    if (!s->api_mel || s->api_n_len <= 0) return fail(Q2W_E_INVALID, "no mel in this state: call q2w_pcm_to_mel or q2w_set_mel first");
+    if (mel_offset < 0) return fail(Q2W_E_INVALID, "negative mel offset");
+    CK(cudaSetDevice(s->m->device));
+    const int64_t t0 = now_us();
+    int rc = ensure_emb(s, 1);
+    if (rc) return rc;
+    // window [offset, offset + 2*n_ctx) of the (already normalised) mel, zero past n_len   (:2264-2285)
+    CKL(mel_to_conv1_operand(s->api_mel, s->api_ld, s->api_n_len, s->n_mel, nullptr, 0, mel_offset, s->T2, 1, s->att, s->stream));
+    if ((rc = forward_from_a1(s, 1, 0))) return rc;
+    CK(cudaStreamSynchronize(s->stream));
+    s->emb_windows = 1;
+    s->t_encode_us += now_us() - t0;
+    s->n_encode++;
+    return Q2W_OK;
+}
+
+static int encode_batch_impl(q2w_state* s, const float* pcm, bool pcm_on_host, size_t stride, const int32_t* n_samples, int B,
+                             float* out_host) {
+    if (!s || !pcm || B <= 0) return fail(Q2W_E_INVALID, "bad argument");
+    if (stride == 0) return fail(Q2W_E_INVALID, "stride must be > 0");
+    CK(cudaSetDevice(s->m->device));
+    const int64_t t0 = now_us();
+    int rc = ensure_emb(s, B);
+    if (rc) return rc;
+    const size_t width = std::min(stride, static_cast<size_t>(s->win_samples));
+    std::vector<int> ns(B);
+    for (int b = 0; b < B; ++b) {
+        int n = n_samples ? n_samples[b] : static_cast<int>(width);
+        if (n < 0 || static_cast<size_t>(n) > width) return fail(Q2W_E_INVALID, "window %d: n_samples %d exceeds the window (%zu samples)", b, n, width);
+        ns[b] = n;
+    }
+    const size_t out_per_window = static_cast<size_t>(s->T / 2) * s->D;
+    for (int w0 = 0; w0 < B; w0 += s->max_batch) {
+        const int Bm = std::min(s->max_batch, B - w0);
+        CK(cudaMemcpyAsync(s->nsamp_dev, ns.data() + w0, sizeof(int) * Bm, cudaMemcpyHostToDevice, s->stream));
+        const float* pcm_dev = nullptr;
+        size_t dev_stride = stride;
+        if (pcm_on_host) {
+            CK(cudaMemcpy2DAsync(s->pcm_dev, static_cast<size_t>(s->win_samples) * sizeof(float), pcm + static_cast<size_t>(w0) * stride,
+                                 stride * sizeof(float), width * sizeof(float), Bm, cudaMemcpyHostToDevice, s->stream));
+            pcm_dev = s->pcm_dev;
+            dev_stride = s->win_samples;
+        } else {
+            pcm_dev = pcm + static_cast<size_t>(w0) * stride;
+        }
+        if ((rc = batch_chunk(s, pcm_dev, dev_stride, Bm, w0))) return rc;
+        if (out_host) {
+            CK(cudaMemcpyAsync(out_host + static_cast<size_t>(w0) * out_per_window, s->emb + static_cast<size_t>(w0) * out_per_window,
+                               static_cast<size_t>(Bm) * out_per_window * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+        }
+    }
+    CK(cudaStreamSynchronize(s->stream));
+    s->emb_windows = B;
+    s->t_encode_us += now_us() - t0;
+    s->n_encode += B;
+    return Q2W_OK;
+}
+
+int q2w_encode_batch_host(q2w_state* s, const float* pcm_host, size_t stride, const int32_t* n_samples, int B, float* out_host) {
+    return encode_batch_impl(s, pcm_host, true, stride, n_samples, B, out_host);
+}
+
+int q2w_encode_batch_device(q2w_state* s, const float* pcm_dev, size_t stride, const int32_t* n_samples_host, int B) {
+    return encode_batch_impl(s, pcm_dev, false, stride, n_samples_host, B, nullptr);
+}
+
+int q2w_embd_dims(const q2w_state* s, int* n_windows, int* n_out, int* n_state) {
+    if (!s) return fail(Q2W_E_INVALID, "null argument");
+    if (n_windows) *n_windows = s->emb_windows;
+    if (n_out) *n_out = s->T / 2;
+    if (n_state) *n_state = s->D;
+    return Q2W_OK;
+}
+
+int q2w_get_embeddings(q2w_state* s, float* out_host, size_t offset_floats, size_t n_floats) {
+    if (!s || !out_host) return fail(Q2W_E_INVALID, "null argument");
+    const size_t total = static_cast<size_t>(s->emb_windows) * (s->T / 2) * s->D;
+    if (!s->emb || offset_floats + n_floats > total) return fail(Q2W_E_INVALID, "embedding range [%zu, %zu) outside the %zu floats available", offset_floats, offset_floats + n_floats, total);
+    CK(cudaSetDevice(s->m->device));
+    CK(cudaMemcpyAsync(out_host, s->emb + offset_floats, n_floats * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    return Q2W_OK;
+}
+
+const float* q2w_embeddings_device(const q2w_state* s) { return s ? s->emb : nullptr; }
+
+int q2w_get_batch_mel(q2w_state* s, int window, float* out_host) {
+    if (!s || !out_host) return fail(Q2W_E_INVALID, "null argument");
+    if (window < 0 || window >= s->max_batch) return fail(Q2W_E_INVALID, "window index out of range");
+    CK(cudaSetDevice(s->m->device));
+    // normalise a copy of the window's log-mel exactly as the conv1 operand builder does
+    float* tmp = nullptr;
+    const size_t n = static_cast<size_t>(s->n_mel) * s->ld_mel;
+    CK(cudaMalloc(&tmp, n * sizeof(float)));
+    cudaError_t e = cudaMemcpyAsync(tmp, s->logmel + static_cast<size_t>(window) * n, n * sizeof(float), cudaMemcpyDeviceToDevice, s->stream);
+    if (e == cudaSuccess) e = mel_normalize(tmp, s->ld_mel, s->T2, s->n_mel, s->winmax + window, 1, s->stream);
+    if (e == cudaSuccess)
+        e = cudaMemcpy2DAsync(out_host, static_cast<size_t>(s->T2) * sizeof(float), tmp, static_cast<size_t>(s->ld_mel) * sizeof(float),
+                              static_cast<size_t>(s->T2) * sizeof(float), s->n_mel, cudaMemcpyDeviceToHost, s->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+    cudaFree(tmp);
+    if (e != cudaSuccess) return fail(Q2W_E_CUDA, "get_batch_mel: %s", cudaGetErrorString(e));
+    return Q2W_OK;
+}
+
+void q2w_get_timings(const q2w_state* s, int64_t* t_mel_us, int64_t* t_encode_us, int32_t* n_encode) {
+    if (!s) return;
+    if (t_mel_us) *t_mel_us = s->t_mel_us;
+    if (t_encode_us) *t_encode_us = s->t_encode_us;
+    if (n_encode) *n_encode = s->n_encode;
+}
+
+void q2w_reset_timings(q2w_state* s) {
+    if (!s) return;
+    s->t_mel_us = s->t_encode_us = 0;
+    s->n_encode = 0;
+}
+
+void* q2w_state_stream(const q2w_state* s) { return s ? static_cast<void*>(s->stream) : nullptr; }
+
+int q2w_sync(q2w_state* s) {
+    if (!s) return fail(Q2W_E_INVALID, "null argument");
+    CK(cudaSetDevice(s->m->device));
+    CK(cudaStreamSynchronize(s->stream));
+    return Q2W_OK;
+}
+
+// =============================================================================================== diagnostics
+const char* q2w_last_error(void) { return g_err; }
+long q2w_kernel_launches(void) { return g_launches.load(); }
+
+int q2w_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    int ok = 0;
+    for (int i = 0; i < n; ++i) {
+        cudaDeviceProp p;
+        if (cudaGetDeviceProperties(&p, i) == cudaSuccess && p.major == 10) ok++;
+    }
+    return ok;
+}
+
+const char* q2w_build_info(void) { return "libq2w_b200: sm_100a, tcgen05/TMEM GEMM + TMA, built " __DATE__ " " __TIME__; }
+
+// =============================================================================================== kernel-level shims
+int q2w_op_gemm(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const float* bias, void* out, int ldo,
+                int epilogue, const float* resid, const float* pos, int pos_period, int scale_cols, float scale, void* stream) {
+    GemmArgs g{};
+    g.A = static_cast<const __half*>(A); g.lda = lda; g.W = static_cast<const __half*>(W); g.ldw = ldw;
+    g.M = M; g.N = N; g.K = K; g.bias = bias; g.out = out; g.ldo = ldo; g.resid = resid; g.pos = pos; g.pos_period = pos_period;
+    g.scale_cols = scale_cols; g.scale = scale;
+    CKL(gemm_f16_tcgen05(g, static_cast<GemmEpilogue>(epilogue), static_cast<cudaStream_t>(stream)));
+    return Q2W_OK;
+}
+
+int q2w_op_layernorm(const float* x, const float* gamma, const float* beta, void* y, int M, int D, float eps, void* stream) {
+    CKL(layernorm_f32_to_f16(x, gamma, beta, static_cast<__half*>(y), M, D, eps, static_cast<cudaStream_t>(stream)));
+    return Q2W_OK;
+}
+
+int q2w_op_pool_layernorm(const float* x, const float* gamma, const float* beta, float* y, int B, int T, int D, float eps, void* stream) {
+    CKL(pool2_layernorm_f32(x, gamma, beta, y, B, T, D, eps, static_cast<cudaStream_t>(stream)));
+    return Q2W_OK;
+}
+
+int q2w_op_attention(const void* qkv, void* out, int B, int T, int H, void* stream) {
+    CKL(attention_f16(static_cast<const __half*>(qkv), static_cast<__half*>(out), B, T, H, static_cast<cudaStream_t>(stream)));
+    return Q2W_OK;
+}
+
+int q2w_op_dequant(const void* src, int ggml_type, void* dst, size_t rows, int K, void* stream) {
+    CKL(dequant_to_f16(src, ggml_type, static_cast<__half*>(dst), rows, K, static_cast<cudaStream_t>(stream)));
+    return Q2W_OK;
+}
+
+int q2w_op_conv2_im2col(const void* h1, void* A2, int B, int T2, int C, void* stream) {
+    CKL(conv2_im2col(static_cast<const __half*>(h1), static_cast<__half*>(A2), B, T2, C, static_cast<cudaStream_t>(stream)));
+    return Q2W_OK;
+}
+
+int q2w_op_mel(const float* filters_host, int n_mel, const float* pcm_dev, size_t stride, const int32_t* n_samples_dev, int n_max,
+               int B, int n_frames, float* logmel_dev, int ld, void* win_max_dev, int normalise, void* stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    MelPlan* plan = nullptr;
+    CK(mel_plan_create(&plan, filters_host, n_mel, 201, st));
+    cudaError_t e = mel_logpower(plan, pcm_dev, stride, n_samples_dev, n_max, B, n_frames, logmel_dev, ld, static_cast<float*>(win_max_dev), st);
+    g_launches.fetch_add(2);
+    if (e == cudaSuccess && normalise) {
+        e = mel_normalize(logmel_dev, ld, n_frames, n_mel, static_cast<const float*>(win_max_dev), B, st);
+        g_launches.fetch_add(1);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    mel_plan_destroy(plan);
+    if (e != cudaSuccess) return fail(Q2W_E_CUDA, "q2w_op_mel: %s", cudaGetErrorString(e));
+    return Q2W_OK;
+}
+
+}  // extern "C"
