@@ -39,25 +39,28 @@ def _dequant(raw: np.ndarray, ttype: int, k: int) -> np.ndarray:
 
 
 def _q8_0_roundtrip(x: np.ndarray) -> np.ndarray:
-    """quantize_row_q8_0 then dequantise: what the CPU backend feeds its int8 dot for Q8_0/Q4_0 weights"""
+    """quantize_row_q8_0 then dequantise: what the CPU backend feeds its int8 dot for Q8_0/Q4_0 weights.
+    This is the vectorised x86 path the backend actually runs (ggml-quants.c:943-1000), which differs from the scalar
+    _ref quantiser in two details: id = 127 / amax (not 1 / d) and round-to-nearest-even (not roundf)."""
     shp = x.shape
     xb = x.reshape(-1, 32).astype(np.float32)
     amax = np.abs(xb).max(axis=1)
     d = (amax / np.float32(127.0)).astype(np.float32)
     with np.errstate(divide="ignore"):
-        inv = np.where(d != 0, np.float32(1.0) / d, np.float32(0)).astype(np.float32)
-    v = (xb * inv[:, None]).astype(np.float64)
-    q = np.trunc(v + np.copysign(0.5, v))
+        inv = np.where(amax != 0, np.float32(127.0) / amax, np.float32(0)).astype(np.float32)
+    q = np.rint((xb * inv[:, None]).astype(np.float32))
     d16 = d.astype(np.float16).astype(np.float32)
     return (q.astype(np.float32) * d16[:, None]).reshape(shp)
 
 
 def gelu_tanh(x: np.ndarray, via_f16: bool) -> np.ndarray:
-    if via_f16:
-        x = x.astype(np.float16).astype(np.float32)
-    y = (0.5 * x * (1.0 + np.tanh(np.float32(0.79788456080286535587989211986876) * x * (1.0 + np.float32(0.044715) * x * x)))).astype(np.float32)
+    """ggml_vec_gelu_f32 (ggml.c:2556-2570): x <= -10 -> 0, x >= 10 -> x, else table[f16(x)] with F16 table entries"""
+    x = np.asarray(x, dtype=np.float32)
+    xin = x.astype(np.float16).astype(np.float32) if via_f16 else x
+    y = (0.5 * xin * (1.0 + np.tanh(np.float32(0.79788456080286535587989211986876) * xin * (1.0 + np.float32(0.044715) * xin * xin)))).astype(np.float32)
     if via_f16:
         y = y.astype(np.float16).astype(np.float32)
+        y = np.where(x <= -10.0, np.float32(0.0), np.where(x >= 10.0, x, y)).astype(np.float32)
     return y
 
 

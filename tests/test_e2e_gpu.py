@@ -1,0 +1,180 @@
+"""-m gpu: PCM -> mel -> encoder parity through the reference-compatible C API (include/qwen2-whisper.h), against
+ (a) golden vectors produced by the unmodified reference's ggml CPU backend (tests/golden, made by make_golden.py),
+ (b) the compiled reference run live on the box's host cores (oracle/_ref), and
+ (c) the numpy restatement (oracle/encoder_np.py) for the "dequantised-weight F32" check of the quantised paths.
+Tolerances: util.TOL."""
+import os
+
+import numpy as np
+import pytest
+
+from util import TOL, max_abs, rel_l2
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+from qwen2_audio_whisper_ggml_b200 import Context, ggml_quant as gq, modelfile as mfm, synth  # noqa: E402
+from qwen2_audio_whisper_ggml_b200 import api  # noqa: E402
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+WT = {"f16": gq.GGML_TYPE_F16, "q8_0": gq.GGML_TYPE_Q8_0, "q4_0": gq.GGML_TYPE_Q4_0, "f32": gq.GGML_TYPE_F32}
+
+
+@pytest.fixture(scope="module", autouse=True)
+def quiet_log():
+    api.log_set(lambda lvl, txt: None)
+    yield
+    api.log_set(None)
+
+
+def tiny_ctx(wname, seed=1):
+    buf = mfm.to_bytes(synth.synth_model(synth.TINY_HPARAMS, WT[wname], seed=seed))
+    return Context.init_from_buffer(buf), buf
+
+
+@pytest.mark.parametrize("wname", ["f16", "q8_0", "q4_0", "f32"])
+def test_tiny_full_vs_golden(wname):
+    g = np.load(os.path.join(GOLD, f"tiny_{wname}.npz"))
+    ctx, _ = tiny_ctx(wname)
+    pcm = synth.synth_pcm(32000, seed=3)
+    assert ctx.full(pcm) == 0
+    assert ctx.n_len() == int(g["n_len"])
+    mel = ctx.get_mel()
+    assert max_abs(mel[:, :220], g["mel"]) < TOL["mel"]["max_abs"]
+    emb = ctx.get_embeddings()
+    assert emb.shape == (1,) + g["emb"].shape
+    tol = TOL["f16" if wname in ("f16", "f32") else wname]
+    assert rel_l2(emb[0], g["emb"]) < tol["rel_l2"], rel_l2(emb[0], g["emb"])
+    assert max_abs(emb[0], g["emb"]) < tol["max_abs"]
+    ctx.free()
+
+
+@pytest.mark.parametrize("wname", ["q8_0", "q4_0"])
+def test_tiny_quant_vs_f32_restatement(wname):
+    """block decode + GEMM are exact: compare with plain F32 math on the dequantised weights (no activation quantisation)"""
+    from oracle import encoder_np, mel_np
+    ctx, buf = tiny_ctx(wname)
+    pcm = synth.synth_pcm(32000, seed=3)
+    assert ctx.full(pcm) == 0
+    mf = mfm.read_model(buf)
+    want = encoder_np.EncoderOracle(mf, "f32").encode(mel_np.window(mel_np.log_mel_spectrogram(pcm, mf.filters), 0, 100))
+    emb = ctx.get_embeddings()[0]
+    t = TOL["quant_vs_f32_restatement"]
+    assert rel_l2(emb, want) < t["rel_l2"], rel_l2(emb, want)
+    assert max_abs(emb, want) < t["max_abs"]
+    ctx.free()
+
+
+def test_tiny_live_reference_offsets_and_set_mel(ref):
+    """whisper_full with offset_ms, whisper_set_mel + whisper_encode, against the reference run live"""
+    ctx, buf = tiny_ctx("f16", seed=7)
+    rctx = ref.RefContext(buf)
+    pcm = synth.synth_pcm(5 * 16000, seed=21, kind="noise")
+    for off_ms in (0, 1000, 2500):
+        assert ctx.full(pcm, offset_ms=off_ms) == 0
+        assert rctx.full(pcm, offset_ms=off_ms) == 0
+        a, b = ctx.get_embeddings()[0], rctx.get_embeddings()
+        assert rel_l2(a, b) < TOL["f16"]["rel_l2"], (off_ms, rel_l2(a, b))
+    mel = rctx.get_mel()
+    assert max_abs(ctx.get_mel(), mel) < TOL["mel"]["max_abs"]
+    # caller-provided mel, window running past n_len is zero-filled (src:2274-2283)
+    short = np.ascontiguousarray(mel[:, :150])
+    assert ctx.set_mel(short, 150, 128) == 0 and rctx.set_mel(short) == 0
+    assert ctx.n_len() == 150
+    assert ctx.encode(40) == 0
+    assert rctx.full(None, offset_ms=400) == 0
+    assert rel_l2(ctx.get_embeddings()[0], rctx.get_embeddings()) < TOL["f16"]["rel_l2"]
+    assert ctx.set_mel(short, 150, 80) == -1          # wrong n_mel is rejected like the reference (:3287)
+    ctx.free()
+    rctx.free()
+
+
+def test_short_audio_returns_zero_and_does_nothing():
+    ctx, _ = tiny_ctx("f16")
+    p = api.wlib().whisper_full_default_params()
+    p.offset_ms = 0
+    p.duration_ms = 500           # < 1000 ms -> warning + 0 (:2362-2365)
+    assert ctx.full(synth.synth_pcm(16000, seed=1), params=p) == 0
+    nw, _, _ = ctx.embd_dims()
+    assert nw == 0
+    ctx.free()
+
+
+def test_batch_equals_single_windows_bitwise():
+    """data-parallel contract: window b of a batch == the same window alone, bit for bit; ragged lengths; chunked micro-batches"""
+    ctx, _ = tiny_ctx("f16")
+    win = 200 * 160
+    B = 5
+    pcm = np.zeros((B, win), dtype=np.float32)
+    ns = np.array([win, win // 2, win, 16000, win - 7], dtype=np.int32)
+    for b in range(B):
+        pcm[b, :ns[b]] = synth.synth_pcm(int(ns[b]), seed=40 + b, kind="chirp" if b % 2 else "noise")
+    assert ctx.set_max_batch(2) == 0
+    out = ctx.encode_batch(pcm, ns)
+    assert ctx.set_max_batch(8) == 0
+    out8 = ctx.encode_batch(pcm, ns)
+    assert np.array_equal(out, out8)
+    for b in range(B):
+        assert ctx.full(pcm[b, :ns[b]]) == 0
+        single = ctx.get_embeddings()[0]
+        # whisper_full computes the mel over n + 30 s of padding, the batch API over one window: same frames, same max
+        assert rel_l2(out[b], single) < 1e-6, (b, rel_l2(out[b], single))
+    ctx.free()
+
+
+def test_loader_error_paths():
+    mf = synth.synth_model(synth.TINY_HPARAMS, gq.GGML_TYPE_F16, seed=1)
+    good = mfm.to_bytes(mf)
+    bad_magic = b"\x00\x00\x00\x00" + good[4:]
+    with pytest.raises(Exception):
+        Context.init_from_buffer(bad_magic)
+    with pytest.raises(Exception):                                  # truncated: not all tensors loaded (:1861)
+        Context.init_from_buffer(mfm.to_bytes(mfm.ModelFile(mf.hparams, mf.filters, [], mf.tensors[:-1])))
+    wrong = list(mf.tensors)
+    t = wrong[0]                                                    # embed_positions.weight [D, T] -> [T, D]
+    wrong[0] = mfm.TensorRec(t.name, t.ttype, t.ne[::-1], t.data)
+    with pytest.raises(Exception):                                  # wrong shape (:1821)
+        Context.init_from_buffer(mfm.to_bytes(mfm.ModelFile(mf.hparams, mf.filters, [], wrong)))
+    unk = list(mf.tensors) + [mfm.TensorRec("decoder.blocks.0.attn.weight", 0, (4,), np.zeros(16, np.uint8))]
+    with pytest.raises(Exception):                                  # unknown tensor (:1807)
+        Context.init_from_buffer(mfm.to_bytes(mfm.ModelFile(mf.hparams, mf.filters, [], unk)))
+    p = api.default_context_params()
+    p.flash_attn = True
+    with pytest.raises(Exception):
+        Context.init_from_buffer(good, p)
+    p = api.default_context_params()
+    p.use_gpu = False
+    with pytest.raises(Exception):
+        Context.init_from_buffer(good, p)
+    Context.init_from_buffer(good).free()
+
+
+@pytest.mark.parametrize("wname", ["f16", "q8_0", "q4_0"])
+def test_full_size_vs_golden(wname):
+    """BASELINE config 0 shape: 32 layers, d=1280, 20 heads, 128 mels, one 30 s window; golden from the reference's CPU backend"""
+    path = os.path.join(GOLD, f"full_{wname}.npz")
+    if not os.path.exists(path):
+        pytest.skip("full-size golden not generated")
+    g = np.load(path)
+    buf = mfm.to_bytes(synth.synth_model(synth.FULL_HPARAMS, WT[wname], seed=1234))
+    ctx = Context.init_from_buffer(buf)
+    del buf
+    pcm = synth.synth_pcm(480000, seed=0)
+    assert ctx.full(pcm) == 0
+    mel = ctx.get_mel()
+    assert mel.shape == (128, 6000)
+    assert max_abs(mel[g["mel_row_idx"]][:, :3000], g["mel_rows"]) < TOL["mel"]["max_abs"]
+    emb = ctx.get_embeddings()[0]
+    assert emb.shape == (750, 1280)
+    tol = TOL[wname]
+    rows = emb[g["emb_row_idx"]]
+    assert rel_l2(rows, g["emb_rows"]) < tol["rel_l2"], rel_l2(rows, g["emb_rows"])
+    assert max_abs(rows, g["emb_rows"]) < tol["max_abs"], max_abs(rows, g["emb_rows"])
+    assert max_abs(emb.mean(axis=0), g["emb_col_mean"]) < tol["max_abs"]
+    # batched path on the same clip (3 copies + a silent window) == single-window path
+    ctx.set_max_batch(4)
+    win = np.stack([pcm, pcm, np.zeros_like(pcm), pcm])
+    out = ctx.encode_batch(win)
+    assert rel_l2(out[0], emb) < 1e-6 and np.array_equal(out[0], out[1]) and np.array_equal(out[0], out[3])
+    assert np.isfinite(out[2]).all()
+    ctx.free()

@@ -1,0 +1,183 @@
+"""-m gpu: every sm_100a kernel against a plain torch FP32 restatement of the same op, through the C-ABI shims."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from util import max_abs, rel_l2
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+from qwen2_audio_whisper_ggml_b200 import ggml_quant as gq  # noqa: E402
+from qwen2_audio_whisper_ggml_b200 import lib as L  # noqa: E402
+from qwen2_audio_whisper_ggml_b200 import synth  # noqa: E402
+
+
+def ck(rc):
+    L.check(rc)
+    torch.cuda.synchronize()
+
+
+def gelu_tanh(x):
+    return 0.5 * x * (1.0 + torch.tanh(0.7978845608028654 * x * (1.0 + 0.044715 * x * x)))
+
+
+GEMM_SHAPES = [(300, 384, 128), (128, 256, 64), (1500, 1280, 1280), (4113, 3840, 1280), (1500, 1280, 5120), (3000, 1280, 384),
+               (777, 128, 512), (200, 136, 240)]
+
+
+@pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
+@pytest.mark.parametrize("epi", [0, 1, 2, 3, 4])
+def test_gemm(lib, M, N, K, epi):
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N * 3 + K + epi)
+    A = (torch.randn(M, K, device="cuda", generator=g) * 0.5).half()
+    W = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).half()
+    bias = torch.randn(N, device="cuda", generator=g) * 0.1
+    acc = A.float() @ W.float().t() + bias
+    period = 100
+    pos = torch.randn(period, N, device="cuda", generator=g)
+    resid = torch.randn(M, N, device="cuda", generator=g)
+    scale_cols, scale = (N // 2) // 8 * 8, 0.125
+    if epi == L.EPI_BIAS_F16:
+        want = acc.clone()
+        want[:, :scale_cols] *= scale
+        out = torch.full((M, N), float("nan"), device="cuda", dtype=torch.half)
+    elif epi == L.EPI_BIAS_GELU_F16:
+        want = gelu_tanh(acc)
+        out = torch.full((M, N), float("nan"), device="cuda", dtype=torch.half)
+    elif epi == L.EPI_BIAS_RESID_F32:
+        want = acc + resid
+        out = resid.clone()          # in place, as the engine uses it
+    elif epi == L.EPI_BIAS_GELU_POS_F32:
+        want = gelu_tanh(acc) + pos[torch.arange(M, device="cuda") % period]
+        out = torch.full((M, N), float("nan"), device="cuda")
+    else:
+        want = acc
+        out = torch.full((M, N), float("nan"), device="cuda")
+    ck(lib.q2w_op_gemm(A.data_ptr(), K, W.data_ptr(), K, M, N, K, bias.data_ptr(), out.data_ptr(), N, epi,
+                       out.data_ptr() if epi == L.EPI_BIAS_RESID_F32 else None, pos.data_ptr(), period, scale_cols, scale, None))
+    got = out.float().cpu().numpy()
+    want = want.cpu().numpy()
+    assert np.isfinite(got).all()
+    tol = 2e-3 if out.dtype == torch.half else 2e-5
+    assert rel_l2(got, want) < tol, (rel_l2(got, want), max_abs(got, want))
+
+
+def test_gemm_strided_operands(lib):
+    """lda / ldw / ldo larger than the logical widths (views into wider buffers)"""
+    M, N, K = 520, 256, 192
+    g = torch.Generator(device="cuda").manual_seed(5)
+    Abig = (torch.randn(M, K + 64, device="cuda", generator=g)).half()
+    Wbig = (torch.randn(N, K + 8, device="cuda", generator=g) / K ** 0.5).half()
+    out = torch.zeros(M, N + 16, device="cuda")
+    ck(lib.q2w_op_gemm(Abig.data_ptr(), K + 64, Wbig.data_ptr(), K + 8, M, N, K, None, out.data_ptr(), N + 16, L.EPI_BIAS_F32,
+                       None, None, 0, 0, 1.0, None))
+    want = Abig[:, :K].float() @ Wbig[:, :K].float().t()
+    assert rel_l2(out[:, :N].cpu().numpy(), want.cpu().numpy()) < 2e-5
+    assert float(out[:, N:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("M,D", [(1, 128), (37, 384), (1500, 1280), (4099, 1280)])
+def test_layernorm(lib, M, D):
+    g = torch.Generator(device="cuda").manual_seed(M + D)
+    x = torch.randn(M, D, device="cuda", generator=g) * 3 + 1.5
+    gam = 1 + 0.1 * torch.randn(D, device="cuda", generator=g)
+    bet = 0.1 * torch.randn(D, device="cuda", generator=g)
+    y = torch.empty(M, D, device="cuda", dtype=torch.half)
+    ck(lib.q2w_op_layernorm(x.data_ptr(), gam.data_ptr(), bet.data_ptr(), y.data_ptr(), M, D, 1e-5, None))
+    want = torch.nn.functional.layer_norm(x.double(), (D,), gam.double(), bet.double(), 1e-5)
+    assert max_abs(y.float().cpu().numpy(), want.cpu().numpy()) < 4e-3     # f16 output rounding at |y| < 8
+    assert rel_l2(y.float().cpu().numpy(), want.cpu().numpy()) < 5e-4
+
+
+@pytest.mark.parametrize("B,T,D", [(1, 100, 128), (3, 1500, 1280)])
+def test_pool_layernorm(lib, B, T, D):
+    g = torch.Generator(device="cuda").manual_seed(B + T)
+    x = torch.randn(B * T, D, device="cuda", generator=g) * 2
+    gam = 1 + 0.1 * torch.randn(D, device="cuda", generator=g)
+    bet = 0.1 * torch.randn(D, device="cuda", generator=g)
+    y = torch.empty(B * T // 2, D, device="cuda")
+    ck(lib.q2w_op_pool_layernorm(x.data_ptr(), gam.data_ptr(), bet.data_ptr(), y.data_ptr(), B, T, D, 1e-5, None))
+    xp = (x.view(B, T // 2, 2, D).double().sum(2) / 2).view(-1, D)
+    want = torch.nn.functional.layer_norm(xp, (D,), gam.double(), bet.double(), 1e-5)
+    assert max_abs(y.cpu().numpy(), want.cpu().numpy()) < 2e-5
+
+
+@pytest.mark.parametrize("B,T,H", [(1, 64, 2), (2, 100, 2), (1, 1500, 20), (3, 333, 4)])
+def test_attention(lib, B, T, H):
+    D = 64 * H
+    g = torch.Generator(device="cuda").manual_seed(B * 100 + T + H)
+    qkv = torch.randn(B * T, 3 * D, device="cuda", generator=g)
+    qkv[:, :D] *= 0.35                      # pre-scaled queries (the QKV epilogue folds 1/sqrt(64))
+    qkv = qkv.half()
+    out = torch.full((B * T, D), float("nan"), device="cuda", dtype=torch.half)
+    ck(lib.q2w_op_attention(qkv.data_ptr(), out.data_ptr(), B, T, H, None))
+    f = qkv.float().view(B, T, 3, H, 64)
+    q, k, v = f[:, :, 0].permute(0, 2, 1, 3), f[:, :, 1].permute(0, 2, 1, 3), f[:, :, 2].permute(0, 2, 1, 3)
+    p = torch.softmax(q @ k.transpose(-1, -2), dim=-1)
+    want = (p @ v).permute(0, 2, 1, 3).reshape(B * T, D)
+    got = out.float().cpu().numpy()
+    assert np.isfinite(got).all()
+    assert rel_l2(got, want.cpu().numpy()) < 2e-3, rel_l2(got, want.cpu().numpy())
+
+
+@pytest.mark.parametrize("ttype", [gq.GGML_TYPE_Q8_0, gq.GGML_TYPE_Q4_0, gq.GGML_TYPE_F32])
+def test_dequant_bit_exact(lib, ttype):
+    rng = np.random.default_rng(ttype)
+    rows, K = 96, 1280
+    w = (rng.standard_normal((rows, K)) * 0.05).astype(np.float32)
+    w[0, :32] = 0.0
+    raw = gq.quantize(w, ttype).reshape(-1)
+    want = gq.dequantize(raw, ttype, K).astype(np.float16)        # decode in F32, one rounding to F16
+    src = torch.from_numpy(raw.copy()).cuda()
+    dst = torch.empty(rows, K, device="cuda", dtype=torch.half)
+    ck(lib.q2w_op_dequant(src.data_ptr(), ttype, dst.data_ptr(), rows, K, None))
+    assert np.array_equal(dst.cpu().numpy().view(np.uint16), want.view(np.uint16))
+
+
+def test_conv2_im2col(lib):
+    B, T2, Cc = 2, 200, 128
+    g = torch.Generator(device="cuda").manual_seed(9)
+    h1 = torch.randn(B * T2, Cc, device="cuda", generator=g).half()
+    A2 = torch.empty(B * T2 // 2, 3 * Cc, device="cuda", dtype=torch.half)
+    ck(lib.q2w_op_conv2_im2col(h1.data_ptr(), A2.data_ptr(), B, T2, Cc, None))
+    x = h1.view(B, T2, Cc).permute(0, 2, 1).float()                                   # [B, C, T2]
+    cols = torch.nn.functional.unfold(x.unsqueeze(2), (1, 3), padding=(0, 1), stride=(1, 2))   # [B, C*3, T]
+    want = cols.permute(0, 2, 1).reshape(B * T2 // 2, 3 * Cc)
+    assert torch.equal(A2.float(), want)
+
+
+@pytest.mark.parametrize("kind,n", [("chirp", 480000), ("tones", 480000), ("silence", 16000), ("noise", 123457), ("chirp", 201)])
+def test_mel_vs_numpy_oracle(lib, kind, n):
+    from oracle import mel_np
+    filt = synth.slaney_mel_filters(128)
+    pcm = synth.synth_pcm(n, seed=11, kind=kind)
+    n_len, _ = mel_np.mel_dims(n)
+    ld = (n_len + 3) // 4 * 4
+    d_pcm = torch.from_numpy(pcm).cuda()
+    d_mel = torch.full((128, ld), float("nan"), device="cuda")
+    d_max = torch.zeros(1, device="cuda", dtype=torch.int32)
+    ck(lib.q2w_op_mel(filt.ctypes.data, 128, d_pcm.data_ptr(), 0, None, n, 1, n_len, d_mel.data_ptr(), ld, d_max.data_ptr(), 1, None))
+    got = d_mel[:, :n_len].cpu().numpy()
+    want = mel_np.log_mel_spectrogram(pcm, filt)
+    assert got.shape == want.shape
+    assert max_abs(got, want) < 2e-4, max_abs(got, want)
+    assert rel_l2(got, want) < 1e-5
+
+
+def test_mel_dense_random_filterbank(lib):
+    """the filter matrix comes from the model file: any dense matrix must be applied exactly, not just banded triangles"""
+    from oracle import mel_np
+    rng = np.random.default_rng(3)
+    filt = (rng.random((128, 201)) * 0.01).astype(np.float32)
+    filt[5] = 0.0
+    pcm = synth.synth_pcm(48000, seed=2, kind="noise")
+    n_len, _ = mel_np.mel_dims(pcm.size)
+    ld = (n_len + 3) // 4 * 4
+    d_pcm = torch.from_numpy(pcm).cuda()
+    d_mel = torch.empty(128, ld, device="cuda")
+    d_max = torch.zeros(1, device="cuda", dtype=torch.int32)
+    ck(lib.q2w_op_mel(filt.ctypes.data, 128, d_pcm.data_ptr(), 0, None, pcm.size, 1, n_len, d_mel.data_ptr(), ld, d_max.data_ptr(), 1, None))
+    want = mel_np.log_mel_spectrogram(pcm, filt)
+    assert max_abs(d_mel[:, :n_len].cpu().numpy(), want) < 2e-4
