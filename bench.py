@@ -1,0 +1,303 @@
+#!/usr/bin/env python
+"""bench.py -- audio-seconds/second of the mel + encoder hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--wtype f16|q8_0|q4_0] [--windows B] [--impl reference]
+
+A step = one pass of the hot path (PCM -> log-mel -> conv stem -> 32 encoder blocks -> pool -> LN) over one batch of
+B synthetic 30 s windows per GPU (default B = 64, F16: BASELINE.json configs[1]).  One process per GPU; for N > 1 launch
+under torchrun (RANK / LOCAL_RANK / WORLD_SIZE); windows are sharded, weights replicated, no collective on the path.
+
+  value        whole-job audio-s/s with the PCM already resident in HBM; CUDA events on the library's stream, max over ranks
+  e2e          the same metric through the reference-facing call (whisper_encode_batch) with pinned HOST buffers:
+               H2D of the PCM and D2H of the embeddings inside the timed region
+  roofline     the dominant kernel (tcgen05 weight GEMM): algorithmic FLOPs / CUDA-event time, measured live in the timed steps
+  cpu_baseline the UNMODIFIED reference (oracle/_ref, ggml CPU backend) on this box's host cores, one window (rank 0, N = 1)
+  --impl reference   times only that reference arm and prints the same line with "impl": "reference"
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "audio_seconds_per_second_mel_plus_encoder"
+UNIT = "audio-s/s"
+WINDOW_S = 30.0
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=d["hbm_gbs"], tflops=d.get("bf16_tflops_sustained", d["bf16_tflops"]), burst=d["bf16_tflops"], src="measured")
+    return dict(hbm_gbs=6650.0, tflops=1400.0, burst=1590.0, src="fallback")
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)"""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.gpu)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        self.join(timeout=2)
+        sm, mx, reasons, power = [], [], set(), []
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2])); power.append(float(r[3]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        if not sm:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0)
+        busy = [s for s, p in zip(sm, power) if p > 300] or sm
+        return dict(sm_mhz=statistics.median(busy), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm), power_w_max=max(power))
+
+
+def build_model_bytes(wtype_name: str, hp=None) -> bytes:
+    from qwen2_audio_whisper_ggml_b200 import ggml_quant as gq, modelfile as mfm, synth
+    wt = {"f16": gq.GGML_TYPE_F16, "q8_0": gq.GGML_TYPE_Q8_0, "q4_0": gq.GGML_TYPE_Q4_0, "f32": gq.GGML_TYPE_F32}[wtype_name]
+    return mfm.to_bytes(synth.synth_model(hp or synth.FULL_HPARAMS, wt, seed=1234))
+
+
+def synth_windows(B: int, rank: int) -> np.ndarray:
+    from qwen2_audio_whisper_ggml_b200 import synth
+    base = [synth.synth_pcm(480000, seed=1000 * rank + i, kind="chirp" if i % 4 else "noise") for i in range(min(B, 8))]
+    out = np.empty((B, 480000), dtype=np.float32)
+    for b in range(B):
+        out[b] = np.roll(base[b % len(base)], 997 * (b // len(base)))
+    return out
+
+
+def run_reference(model_bytes: bytes, steps: int, warmup: int, threads: int):
+    """the unmodified reference (ggml CPU backend) on host cores: one 30 s window per step"""
+    from oracle import refbind
+    from qwen2_audio_whisper_ggml_b200 import synth
+    ctx = refbind.RefContext(model_bytes)
+    pcm = synth.synth_pcm(480000, seed=0)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        rc = ctx.full(pcm, n_threads=threads)
+        dt = time.perf_counter() - t0
+        if rc != 0:
+            raise RuntimeError(f"reference whisper_full -> {rc}")
+        if i >= warmup:
+            times.append(dt)
+    ctx.free()
+    return times
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--wtype", default="f16", choices=["f16", "q8_0", "q4_0"])
+    ap.add_argument("--windows", type=int, default=64, help="30 s windows per GPU per step")
+    ap.add_argument("--max-batch", type=int, default=0, help="windows per micro-batch (default: = --windows)")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-threads", type=int, default=0)
+    a = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    threads = a.cpu_threads or (os.cpu_count() or 1)
+    workload = (f"BASELINE configs[1]: Qwen2-Audio encoder {a.wtype.upper()} (32L, d=1280, 20 heads, 128 mel), "
+                f"{a.windows} x 30 s windows per GPU, mel + encoder")
+    config = {"workload": workload, "windows_per_gpu": a.windows, "weights": a.wtype, "sharding": f"dp{world} (independent windows, replicated weights, no collective)",
+              "l2": "no explicit flush: each step streams ~2.7 GB of activations + 1.26 GB of weights, >> 126 MB L2"}
+
+    # ------------------------------------------------------------------ reference arm
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        mb = build_model_bytes(a.wtype)
+        times = run_reference(mb, a.steps, a.warmup, threads)
+        sec = statistics.median(times)
+        val = WINDOW_S / sec
+        sample = f"1 x 30 s window per step ({a.steps} steps, p50), {a.wtype} weights, n_threads={threads}"
+        print(json.dumps({"metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+                          "ms_per_step": 1e3 * sec, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
+                          "data": "synthetic", "impl": "reference", "config": config,
+                          "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "reference", "sample": sample},
+                          "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    # ------------------------------------------------------------------ B200 arm
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    from qwen2_audio_whisper_ggml_b200 import Context, api
+    from qwen2_audio_whisper_ggml_b200 import lib as L
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (there is no CPU fallback for the product arm; use --impl reference)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    lib = L.load_library()
+    api.log_set(lambda lvl, txt: None)
+
+    t_setup = time.time()
+    mb = build_model_bytes(a.wtype)
+    cp = api.default_context_params()
+    cp.gpu_device = local_rank
+    ctx = Context.init_from_buffer(mb, cp)
+    B = a.windows
+    assert ctx.set_max_batch(a.max_batch or B) == 0
+    st = ctx.q2w_state()
+    stream = torch.cuda.ExternalStream(lib.q2w_state_stream(st), device=torch.device("cuda", local_rank))
+    host = torch.from_numpy(synth_windows(B, rank)).pin_memory()
+    dev = host.cuda()
+    out_host = torch.empty((B, 750, 1280), dtype=torch.float32).pin_memory()
+    torch.cuda.synchronize()
+    setup_s = time.time() - t_setup
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device():
+        rc = ctx.encode_batch_device(dev.data_ptr(), 480000, B)
+        if rc != 0:
+            raise RuntimeError("whisper_encode_batch_device failed")
+
+    def step_host():
+        ctx.encode_batch(host.numpy(), out=out_host.numpy())
+
+    # ---- device-resident throughput ("value") with the live per-kernel roofline
+    for _ in range(a.warmup):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.25)
+    L.check(lib.q2w_profile_enable(st, 1))
+    launches0 = lib.q2w_kernel_launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for _ in range(a.steps):
+        step_device()
+    e1.record(stream)
+    barrier()
+    dev_ms = e0.elapsed_time(e1)
+    launches = lib.q2w_kernel_launches() - launches0
+    clocks = sampler.stop()
+
+    prof = {}
+    names = ["gemm", "attention", "layernorm", "mel", "im2col", "dequant"]
+    for ci, nm in enumerate(names):
+        ms, cnt, fl, by = C.c_double(), C.c_long(), C.c_double(), C.c_double()
+        L.check(lib.q2w_profile_read(st, ci, C.byref(ms), C.byref(cnt), C.byref(fl), C.byref(by)))
+        prof[nm] = dict(ms=ms.value, count=cnt.value, flops=fl.value, bytes=by.value)
+    L.check(lib.q2w_profile_enable(st, 0))
+
+    # ---- end-to-end through the reference-facing API with host buffers
+    for _ in range(max(1, min(a.warmup, 2))):
+        step_host()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        step_host()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+
+    # ---- single-window latency (p50 ms per 30 s window, B = 1), device-resident PCM
+    lat = []
+    for i in range(23):
+        barrier() if i == 0 else None
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record(stream)
+        ctx.encode_batch_device(dev.data_ptr(), 480000, 1)
+        a1.record(stream)
+        torch.cuda.synchronize()
+        if i >= 3:
+            lat.append(a0.elapsed_time(a1))
+
+    t = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_s = float(t[0]), float(t[1])
+    total_audio = WINDOW_S * B * world * a.steps
+    value = total_audio / (dev_ms / 1e3)
+    e2e_value = total_audio / e2e_s
+
+    pk = peaks()
+    g = prof["gemm"]
+    gemm_tflops = g["flops"] / (g["ms"] * 1e-3) / 1e12 if g["ms"] > 0 else 0.0
+    roofline = {"bound": "tensor", "kernel": "gemm_kernel<EPI> (tcgen05.mma kind::f16, TMA, TMEM)", "achieved": gemm_tflops, "peak": pk["tflops"],
+                "unit": "TFLOP/s", "frac": gemm_tflops / pk["tflops"], "peak_source": f"{pk['src']} bf16_tflops_sustained (kernel timed inside a long step)",
+                "traffic": None, "launches": g["count"], "avg_launch_ms": g["ms"] / max(1, g["count"]),
+                "flops_per_launch": g["flops"] / max(1, g["count"]), "share_of_step": g["ms"] / dev_ms}
+    kernels = {}
+    for nm, p in prof.items():
+        if p["count"] == 0:
+            continue
+        kernels[nm] = {"ms_per_step": p["ms"] / a.steps, "launches_per_step": p["count"] / a.steps, "share": p["ms"] / dev_ms}
+        if p["flops"] > 0:
+            kernels[nm]["tflops"] = p["flops"] / (p["ms"] * 1e-3) / 1e12
+        if p["bytes"] > 0 and p["flops"] == 0:
+            kernels[nm]["gbs"] = p["bytes"] / (p["ms"] * 1e-3) / 1e9
+            kernels[nm]["hbm_frac"] = kernels[nm]["gbs"] / pk["hbm_gbs"]
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        try:
+            times = run_reference(mb, 1, 1, threads)
+            cpu_baseline = {"value": WINDOW_S / times[0], "unit": UNIT, "cores": threads, "kind": "reference",
+                            "sample": f"1 x 30 s window (1/{B} of a step) after 1 warm-up window, {a.wtype} weights, unmodified reference ggml CPU backend (oracle/_ref), n_threads={threads}",
+                            "seconds_per_window": times[0]}
+        except Exception as ex:  # the checker is optional for the product arm
+            cpu_baseline = {"value": None, "unit": UNIT, "cores": threads, "kind": "reference", "sample": f"unavailable: {ex}"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+                "ms_per_step": dev_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
+                "data": "synthetic", "config": config, "clocks": clocks,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(host.numel() * 4), "d2h_bytes_per_step": int(out_host.numel() * 4),
+                        "ms_per_step": 1e3 * e2e_s / a.steps},
+                "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline, "kernels": kernels,
+                "p50_ms_per_window_b1": statistics.median(lat), "ms_per_window": dev_ms / a.steps / B,
+                "tflops_whole_step": 2.2738 * B * a.steps / (dev_ms / 1e3) / 1e0 * 1.0, "setup_s": setup_s}
+        line["tflops_whole_step"] = 2.2738e12 * B * a.steps / (dev_ms / 1e3) / 1e12
+        print(json.dumps(line))
+    ctx.free()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -104,6 +104,11 @@ Q2W_API int  q2w_get_batch_mel(q2w_state* s, int window, float* out_host /* [n_m
 /* timers with the reference's meaning (t_mel_us, t_encode_us, n_encode: :796-809, :2651, :2335) */
 Q2W_API void q2w_get_timings(const q2w_state* s, int64_t* t_mel_us, int64_t* t_encode_us, int32_t* n_encode);
 Q2W_API void q2w_reset_timings(q2w_state* s);
+/* per-kernel-class device timing with CUDA events recorded on the state's stream (bench.py's live roofline).
+ * classes: 0 weight GEMMs (tcgen05), 1 attention, 2 LayerNorm (+pool tail), 3 mel, 4 im2col/operand builders, 5 ggml block decode.
+ * total_flops / total_bytes are the ALGORITHMIC figures of DESIGN.md for the launches recorded since enable(1). */
+Q2W_API int  q2w_profile_enable(q2w_state* s, int on);
+Q2W_API int  q2w_profile_read(q2w_state* s, int kernel_class, double* total_ms, long* count, double* total_flops, double* total_bytes);
 /* the stream all work of this state is enqueued on (cudaStream_t), for callers that time with CUDA events */
 Q2W_API void* q2w_state_stream(const q2w_state* s);
 Q2W_API int  q2w_sync(q2w_state* s);

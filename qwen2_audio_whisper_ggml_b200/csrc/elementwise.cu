@@ -247,7 +247,7 @@ cudaError_t conv2_im2col(const __half* h1, __half* A2, int B, int T2, int C, cud
 }
 
 cudaError_t dequant_to_f16(const void* src, int ggml_type, __half* dst, size_t rows, int K, cudaStream_t st) {
-    if (K % 32) return cudaErrorInvalidValue;
+    if (ggml_type != 0 && (K % 32)) return cudaErrorInvalidValue;   // quantised rows are whole 32-element blocks
     const size_t nblocks = rows * static_cast<size_t>(K / 32);
     const unsigned grid = static_cast<unsigned>((nblocks + 255) / 256);
     switch (ggml_type) {

@@ -128,6 +128,11 @@ struct q2w_state {
     // timers
     int64_t t_mel_us = 0, t_encode_us = 0;
     int32_t n_encode = 0;
+    // optional per-kernel-class CUDA-event timing (bench.py roofline): records live on the stream the kernels run on
+    struct ProfRec { int cls; double flops; double bytes; cudaEvent_t a, b; };
+    bool prof_on = false;
+    std::vector<ProfRec> prof;
+    size_t prof_used = 0;
 };
 
 namespace {
@@ -159,15 +164,36 @@ int check_device(int device) {
     return Q2W_OK;
 }
 
+struct ProfScope {
+    q2w_state* s;
+    long idx = -1;   // index, not pointer: the record vector may grow while a scope is open
+    ProfScope(q2w_state* s_, int cls, double flops, double bytes) : s(s_) {
+        if (!s->prof_on) return;
+        if (s->prof_used == s->prof.size()) {
+            q2w_state::ProfRec n{};
+            if (cudaEventCreate(&n.a) != cudaSuccess || cudaEventCreate(&n.b) != cudaSuccess) return;
+            s->prof.push_back(n);
+        }
+        idx = static_cast<long>(s->prof_used++);
+        q2w_state::ProfRec& r = s->prof[idx];
+        r.cls = cls; r.flops = flops; r.bytes = bytes;
+        cudaEventRecord(r.a, s->stream);
+    }
+    ~ProfScope() { if (idx >= 0) cudaEventRecord(s->prof[idx].b, s->stream); }
+};
+enum { PC_GEMM = 0, PC_ATTN = 1, PC_LN = 2, PC_MEL = 3, PC_IM2COL = 4, PC_DEQUANT = 5, PC_COUNT = 6 };
+
 // y = A x W^T with W in the model's device type: quantised matrices are decoded to f16 into the (L2-resident) scratch first
 int weight_gemm(q2w_state* s, const __half* A, int lda, const void* W, int wtype_dev, int M, int N, int K, const float* bias,
                 void* out, int ldo, GemmEpilogue epi, const float* resid, const float* pos, int pos_period, int scale_cols,
                 float scale) {
     const __half* Wh = static_cast<const __half*>(W);
     if (wtype_dev != Q2W_TYPE_F16) {
+        ProfScope ps(s, PC_DEQUANT, 0.0, static_cast<double>(type_row_bytes(wtype_dev, K)) * N + 2.0 * N * K);
         CKL(dequant_to_f16(W, wtype_dev, s->wscratch, static_cast<size_t>(N), K, s->stream));
         Wh = s->wscratch;
     }
+    ProfScope ps(s, PC_GEMM, 2.0 * M * static_cast<double>(N) * K, 0.0);
     GemmArgs g{};
     g.A = A; g.lda = lda; g.W = Wh; g.ldw = K; g.M = M; g.N = N; g.K = K; g.bias = bias; g.out = out; g.ldo = ldo;
     g.resid = resid; g.pos = pos; g.pos_period = pos_period; g.scale_cols = scale_cols; g.scale = scale;
@@ -190,7 +216,10 @@ int forward_from_a1(q2w_state* s, int Bm, int w0) {
                           static_cast<const float*>(m->conv1_b.d), h1, D, EPI_BIAS_GELU_F16, nullptr, nullptr, 0, 0, 1.f)))
         return rc;
     // conv2 (k3 s2 p1) + bias + GELU, transposed to time-major and + positional embedding   (:1927-1930, :2001-2005)
-    CKL(conv2_im2col(h1, A2, Bm, T2, D, s->stream));
+    {
+        ProfScope ps(s, PC_IM2COL, 0.0, 2.0 * Bm * (static_cast<double>(T2) * D + static_cast<double>(T) * 3 * D));
+        CKL(conv2_im2col(h1, A2, Bm, T2, D, s->stream));
+    }
     if ((rc = weight_gemm(s, A2, 3 * D, m->conv2_w.d, Q2W_TYPE_F16, M, D, 3 * D, static_cast<const float*>(m->conv2_b.d),
                           s->x, D, EPI_BIAS_GELU_POS_F32, nullptr, static_cast<const float*>(m->pe.d), T, 0, 1.f)))
         return rc;
@@ -198,20 +227,29 @@ int forward_from_a1(q2w_state* s, int Bm, int w0) {
     for (int il = 0; il < m->hp.n_audio_layer; ++il) {
         Layer& L = m->layers[il];
         // pre-LN + fused QKV projection (+bias, Q * KQscale)   (:2019-2055)
-        CKL(layernorm_f32_to_f16(s->x, static_cast<const float*>(L.ln1_w.d), static_cast<const float*>(L.ln1_b.d), s->ln, M, D,
-                                 eps, s->stream));
+        {
+            ProfScope ps(s, PC_LN, 0.0, 6.0 * M * D);
+            CKL(layernorm_f32_to_f16(s->x, static_cast<const float*>(L.ln1_w.d), static_cast<const float*>(L.ln1_b.d), s->ln, M, D,
+                                     eps, s->stream));
+        }
         if ((rc = weight_gemm(s, s->ln, D, L.qkv_w, m->wtype_dev, M, 3 * D, D, L.qkv_b, s->qkv, 3 * D, EPI_BIAS_F16, nullptr,
                               nullptr, 0, D, kq_scale)))
             return rc;
         // softmax(Q K^T) V per head   (:2080-2106)
-        CKL(attention_f16(s->qkv, s->att, Bm, T, H, s->stream));
+        {
+            ProfScope ps(s, PC_ATTN, 4.0 * Bm * static_cast<double>(T) * T * D, 8.0 * M * D);
+            CKL(attention_f16(s->qkv, s->att, Bm, T, H, s->stream));
+        }
         // out-proj + bias + residual   (:2112-2120)
         if ((rc = weight_gemm(s, s->att, D, L.o_w.d, m->wtype_dev, M, D, D, static_cast<const float*>(L.o_b.d), s->x, D,
                               EPI_BIAS_RESID_F32, s->x, nullptr, 0, 0, 1.f)))
             return rc;
         // MLP: LN, fc1 + GELU, fc2 + residual   (:2128-2154)
-        CKL(layernorm_f32_to_f16(s->x, static_cast<const float*>(L.ln2_w.d), static_cast<const float*>(L.ln2_b.d), s->ln, M, D,
-                                 eps, s->stream));
+        {
+            ProfScope ps(s, PC_LN, 0.0, 6.0 * M * D);
+            CKL(layernorm_f32_to_f16(s->x, static_cast<const float*>(L.ln2_w.d), static_cast<const float*>(L.ln2_b.d), s->ln, M, D,
+                                     eps, s->stream));
+        }
         if ((rc = weight_gemm(s, s->ln, D, L.fc1_w.d, m->wtype_dev, M, FF, D, static_cast<const float*>(L.fc1_b.d), s->h, FF,
                               EPI_BIAS_GELU_F16, nullptr, nullptr, 0, 0, 1.f)))
             return rc;
@@ -221,6 +259,7 @@ int forward_from_a1(q2w_state* s, int Bm, int w0) {
     }
     // avg-pool(2,2) over time + final LayerNorm   (:2160-2181)
     float* out = s->emb + static_cast<size_t>(w0) * (T / 2) * D;
+    ProfScope ps(s, PC_LN, 0.0, 6.0 * M * D);
     CKL(pool2_layernorm_f32(s->x, static_cast<const float*>(m->ln_w.d), static_cast<const float*>(m->ln_b.d), out, Bm, T, D, eps,
                             s->stream));
     return Q2W_OK;
@@ -239,10 +278,17 @@ int ensure_emb(q2w_state* s, int n_windows) {
 
 // mel + conv1 operand for Bm windows resident in s->pcm_dev, then the encoder
 int batch_chunk(q2w_state* s, const float* pcm_dev, size_t stride, int Bm, int w0) {
-    CKL(mel_logpower(s->m->mel, pcm_dev, stride, s->nsamp_dev, s->win_samples, Bm, s->n_frames_batch, s->logmel, s->ld_mel,
-                     s->winmax, s->stream));
-    g_launches.fetch_add(1);  // mel_logpower issues two kernels (key init + main)
-    CKL(mel_to_conv1_operand(s->logmel, s->ld_mel, s->n_frames_batch, s->n_mel, s->winmax, 1, 0, s->T2, Bm, s->att, s->stream));
+    {
+        // algorithmic bytes: PCM in + used mel frames out (4*480000 + 4*128*3000 per window)
+        ProfScope ps(s, PC_MEL, 0.0, static_cast<double>(Bm) * (4.0 * s->win_samples + 4.0 * s->n_mel * s->T2));
+        CKL(mel_logpower(s->m->mel, pcm_dev, stride, s->nsamp_dev, s->win_samples, Bm, s->n_frames_batch, s->logmel, s->ld_mel,
+                         s->winmax, s->stream));
+        g_launches.fetch_add(1);  // mel_logpower issues two kernels (key init + main)
+    }
+    {
+        ProfScope ps(s, PC_IM2COL, 0.0, static_cast<double>(Bm) * s->T2 * s->n_mel * (4.0 + 6.0));
+        CKL(mel_to_conv1_operand(s->logmel, s->ld_mel, s->n_frames_batch, s->n_mel, s->winmax, 1, 0, s->T2, Bm, s->att, s->stream));
+    }
     return forward_from_a1(s, Bm, w0);
 }
 
@@ -465,6 +511,7 @@ void q2w_state_free(q2w_state* s) {
     void* ptrs[] = {s->x, s->ln, s->qkv, s->att, s->h, s->wscratch, s->pcm_dev, s->nsamp_dev, s->logmel, s->winmax,
                     s->emb, s->api_mel, s->api_pcm, s->api_max};
     for (void* p : ptrs) if (p) cudaFree(p);
+    for (auto& r : s->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
 }
@@ -649,6 +696,35 @@ void q2w_reset_timings(q2w_state* s) {
     if (!s) return;
     s->t_mel_us = s->t_encode_us = 0;
     s->n_encode = 0;
+}
+
+int q2w_profile_enable(q2w_state* s, int on) {
+    if (!s) return fail(Q2W_E_INVALID, "null argument");
+    CK(cudaSetDevice(s->m->device));
+    CK(cudaStreamSynchronize(s->stream));
+    s->prof_on = on != 0;
+    s->prof_used = 0;
+    return Q2W_OK;
+}
+
+int q2w_profile_read(q2w_state* s, int cls, double* total_ms, long* count, double* total_flops, double* total_bytes) {
+    if (!s || cls < 0 || cls >= PC_COUNT) return fail(Q2W_E_INVALID, "bad argument");
+    CK(cudaSetDevice(s->m->device));
+    CK(cudaStreamSynchronize(s->stream));
+    double ms = 0, fl = 0, by = 0;
+    long n = 0;
+    for (size_t i = 0; i < s->prof_used; ++i) {
+        const auto& r = s->prof[i];
+        if (r.cls != cls) continue;
+        float t = 0.f;
+        CK(cudaEventElapsedTime(&t, r.a, r.b));
+        ms += t; fl += r.flops; by += r.bytes; n++;
+    }
+    if (total_ms) *total_ms = ms;
+    if (count) *count = n;
+    if (total_flops) *total_flops = fl;
+    if (total_bytes) *total_bytes = by;
+    return Q2W_OK;
 }
 
 void* q2w_state_stream(const q2w_state* s) { return s ? static_cast<void*>(s->stream) : nullptr; }

@@ -55,6 +55,8 @@ _SIGS = {
     "q2w_get_batch_mel": (_i, [_vp, _i, _vp]),
     "q2w_get_timings": (None, [_vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
     "q2w_reset_timings": (None, [_vp]),
+    "q2w_profile_enable": (_i, [_vp, _i]),
+    "q2w_profile_read": (_i, [_vp, _i, C.POINTER(C.c_double), C.POINTER(C.c_long), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "q2w_state_stream": (_vp, [_vp]),
     "q2w_sync": (_i, [_vp]),
     "q2w_last_error": (C.c_char_p, []),
