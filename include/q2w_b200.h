@@ -128,6 +128,8 @@ Q2W_API int q2w_op_layernorm(const float* x, const float* gamma, const float* be
 Q2W_API int q2w_op_pool_layernorm(const float* x, const float* gamma, const float* beta, float* y, int B, int T, int D,
                                   float eps, void* stream);
 Q2W_API int q2w_op_attention(const void* qkv_f16, void* out_f16, int B, int T, int H, void* stream);
+/* the mma.sync bring-up kernel, kept as the legacy-tensor-path baseline for tests / profiles only (never on the product path) */
+Q2W_API int q2w_op_attention_legacy_mma(const void* qkv_f16, void* out_f16, int B, int T, int H, void* stream);
 Q2W_API int q2w_op_dequant(const void* src, int ggml_type, void* dst_f16, size_t rows, int K, void* stream);
 Q2W_API int q2w_op_conv2_im2col(const void* h1_f16, void* A2_f16, int B, int T2, int C, void* stream);
 /* mel: filters host [n_mel][201]; pcm device; logmel device [B][n_mel][ld]; win_max device int32[B] (ordered keys) */

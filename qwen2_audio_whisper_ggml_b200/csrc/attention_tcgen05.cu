@@ -1,0 +1,335 @@
+// attention_tcgen05.cu -- fused non-causal self-attention on the 5th-gen tensor cores (sm_100a).
+//
+// Replaces the reference's per-head  KQ = mul_mat(K, Q) ; soft_max(KQ) ; mul_mat(V, KQ_soft_max)  chain and the
+// permute/cont copies around it (/root/reference/src/qwen2-whisper.cpp:2052-2106; the flash_attn branch there is an empty
+// stub).  Q arrives pre-multiplied by 1/sqrt(64) (ggml_scale :2054 folded into the QKV GEMM epilogue).
+// Softmax follows ggml_soft_max (ggml/src/ggml.c:13854-13940): scale 1, no mask, row max subtracted, normalised by the
+// row sum; it is evaluated online in FP32, probabilities are rounded to F16 for the PV product, FP32 accumulation.
+//
+// One CTA = 128 query rows of one (window, head); 256 threads; two CTAs are resident per SM (256 TMEM columns each) so one
+// CTA's softmax (MUFU-bound) overlaps the other's MMAs.
+//   warp 0      TMA producer: Q once, then K_j / V_j tiles (128 x 64 f16, SWIZZLE_128B) through a 3-D tensor map over
+//               qkv[B][T][3D] -- rows past T are out of bounds for the map and arrive as zeros, never as the next window
+//   warp 1      MMA issuer:  S = Q K_j^T   tcgen05.mma kind::f16  M128 N128 K16 x4   (A, B K-major)          -> TMEM cols [0,128)
+//                            O += P_j V_j  tcgen05.mma kind::f16  M128 N64  K16 x8   (A = P K-major from smem,
+//                                                                                      B = V MN-major as loaded) -> TMEM cols [128,192)
+//   warps 4-7   softmax, one thread per query row: tcgen05.ld the S row (single pass, 128 registers), mask the ragged last
+//               tile, running max / sum in the log2 domain, ex2, pack to F16, write the P row into the swizzled smem tile.
+//               O stays in TMEM for the whole KV loop; it is rescaled (tcgen05.ld -> mul -> tcgen05.st) only when the
+//               running max grew by more than 2^8 since the last rescale -- the stale max is exact algebra, it only bounds
+//               the magnitude of P (<= 256 in F16), and the final division by the row sum uses the same reference point.
+// Registers are rebalanced with setmaxnreg (producer/MMA warpgroup 56, softmax warpgroup 200).
+#include "ops.h"
+#include "ptx.cuh"
+
+#include <mutex>
+
+namespace q2w {
+
+namespace {
+
+constexpr int HD = 64, BQ = 128, BKV = 128;
+constexpr int THREADS = 256;
+constexpr int TILE_BYTES = 128 * 128;           // 128 rows x 64 f16 = 16 KB
+constexpr int P_BYTES = 2 * TILE_BYTES;         // 128 x 128 f16 as two K-major 64-column chunks
+constexpr int SMEM_DATA = 3 * TILE_BYTES + P_BYTES;   // Q, K, V, P = 80 KB
+constexpr int SMEM_BYTES = SMEM_DATA + 1024 /*align*/ + 128 /*barriers*/;
+constexpr int TMEM_COLS = 256;
+constexpr int S_COL = 0, O_COL = 128;
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr float RESCALE_THRESHOLD = 8.0f;       // log2 units
+
+// MN-major operand tile written by TMA with SWIZZLE_128B: each K row is 128 B (64 f16 along N), 8-row groups 1024 B apart
+__device__ __forceinline__ uint64_t make_sw128_mnmajor_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+    d |= static_cast<uint64_t>(TILE_BYTES >> 4) << 16;   // LBO: stride between 64-element MN atoms (unused: N = 64 is one atom)
+    d |= static_cast<uint64_t>(1024 >> 4) << 32;         // SBO: stride between 8-row K groups
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(2) << 61;
+    return d;
+}
+
+__device__ __forceinline__ float ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+__device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]),
+        "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]),
+        "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__global__ void __launch_bounds__(THREADS, 2)
+attention_tc_kernel(const __grid_constant__ CUtensorMap tm, __half* __restrict__ out, int T, int D) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sQ = smem;
+    uint8_t* sK = smem + TILE_BYTES;
+    uint8_t* sV = smem + 2 * TILE_BYTES;
+    uint8_t* sP = smem + 3 * TILE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SMEM_DATA);
+    uint64_t* q_full = bars + 0;
+    uint64_t* k_full = bars + 1;
+    uint64_t* k_empty = bars + 2;
+    uint64_t* v_full = bars + 3;
+    uint64_t* pv_done = bars + 4;   // PV_j complete: V and P buffers free, O_j accumulated
+    uint64_t* s_full = bars + 5;
+    uint64_t* s_empty = bars + 6;   // softmax has pulled S_j into registers
+    uint64_t* p_full = bars + 7;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * BQ, h = blockIdx.y, b = blockIdx.z;
+    const int n_kv = (T + BKV - 1) / BKV;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tm);
+        mbar_init(q_full, 1);
+        mbar_init(k_full, 1);
+        mbar_init(k_empty, 1);
+        mbar_init(v_full, 1);
+        mbar_init(pv_done, 1);
+        mbar_init(s_full, 1);
+        mbar_init(s_empty, 128);
+        mbar_init(p_full, 128);
+        fence_mbar_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < 4) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        if (warp == 0 && lane == 0) {
+            // ------------------------------------------------------------ TMA producer
+            mbar_expect_tx(q_full, TILE_BYTES);
+            tma_load_3d(sQ, &tm, q_full, h * HD, q0, b);
+            for (int j = 0; j < n_kv; ++j) {
+                if (j > 0) mbar_wait(k_empty, (j - 1) & 1);
+                mbar_expect_tx(k_full, TILE_BYTES);
+                tma_load_3d(sK, &tm, k_full, D + h * HD, j * BKV, b);
+                if (j > 0) mbar_wait(pv_done, (j - 1) & 1);
+                mbar_expect_tx(v_full, TILE_BYTES);
+                tma_load_3d(sV, &tm, v_full, 2 * D + h * HD, j * BKV, b);
+            }
+        } else if (warp == 1 && lane == 0) {
+            // ------------------------------------------------------------ MMA issuer
+            constexpr uint32_t idesc_qk = make_idesc_f16(BQ, BKV, 0, 0);
+            constexpr uint32_t idesc_pv = make_idesc_f16(BQ, HD, 0, 1);     // B = V is MN-major
+            const uint64_t q_desc = make_sw128_kmajor_desc(smem_u32(sQ));
+            const uint64_t k_desc = make_sw128_kmajor_desc(smem_u32(sK));
+            const uint64_t p_desc = make_sw128_kmajor_desc(smem_u32(sP));
+            const uint64_t v_desc = make_sw128_mnmajor_desc(smem_u32(sV));
+            mbar_wait(q_full, 0);
+            for (int j = 0; j < n_kv; ++j) {
+                mbar_wait(k_full, j & 1);
+                if (j > 0) mbar_wait(s_empty, (j - 1) & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int k = 0; k < HD / 16; ++k)
+                    umma_f16_ss(tmem_base + S_COL, q_desc + 2 * k, k_desc + 2 * k, idesc_qk, k != 0);
+                umma_commit(s_full);
+                umma_commit(k_empty);
+                mbar_wait(p_full, j & 1);
+                mbar_wait(v_full, j & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int k = 0; k < BKV / 16; ++k) {
+                    // P: two 64-column K-major chunks of 16 KB, 32 B per 16-element K step inside a chunk
+                    const uint64_t pa = p_desc + static_cast<uint64_t>((k >> 2) * (TILE_BYTES >> 4) + (k & 3) * 2);
+                    // V: 16 K rows (kv) per step = 2 KB
+                    const uint64_t vb = v_desc + static_cast<uint64_t>(k * (2048 >> 4));
+                    umma_f16_ss(tmem_base + O_COL, pa, vb, idesc_pv, (j | k) != 0);
+                }
+                umma_commit(pv_done);
+            }
+        }
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
+        // ------------------------------------------------------------ softmax (thread = query row)
+        const int qd = warp & 3;
+        const int row = qd * 32 + lane;
+        const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(qd * 32) << 16);
+        float m_used = -INFINITY;   // reference point of P and O, log2 domain
+        float l_sum = 0.f;
+        for (int j = 0; j < n_kv; ++j) {
+            mbar_wait(s_full, j & 1);
+            tc_fence_after();
+            uint32_t s[4][32];
+#pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4) tmem_ld_32x32b_x32(t_lane + S_COL + c4 * 32, s[c4]);
+            tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive(s_empty);
+            // ---- row max (log2 domain), ragged last tile masked
+            const int valid = T - j * BKV;   // >= 1
+            float mx = -INFINITY;
+            if (valid < BKV) {               // warp-uniform
+#pragma unroll
+                for (int c4 = 0; c4 < 4; ++c4)
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (c4 * 32 + i >= valid) s[c4][i] = __float_as_uint(-INFINITY);
+            }
+#pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4)
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const float v = __uint_as_float(s[c4][i]) * LOG2E;
+                    s[c4][i] = __float_as_uint(v);
+                    mx = fmaxf(mx, v);
+                }
+            // ---- lazy rescale decision (warp-uniform because tcgen05.ld/st are warp-collective)
+            float factor = 1.0f;
+            bool need = false;
+            if (j == 0) {
+                m_used = mx;
+            } else if (mx - m_used > RESCALE_THRESHOLD) {
+                need = true;
+                factor = ex2(m_used - mx);
+                m_used = mx;
+                l_sum *= factor;
+            }
+            const bool any_need = __any_sync(0xffffffffu, need);
+            // ---- probabilities
+            float rs = 0.f;
+            uint32_t pk[4][16];
+#pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4)
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                    const float p0 = ex2(__uint_as_float(s[c4][i]) - m_used);
+                    const float p1 = ex2(__uint_as_float(s[c4][i + 1]) - m_used);
+                    rs += p0 + p1;
+                    __half2 hh = __floats2half2_rn(p0, p1);
+                    pk[c4][i >> 1] = *reinterpret_cast<uint32_t*>(&hh);
+                }
+            l_sum += rs;
+            // ---- P and V buffers free, O_{j-1} accumulated
+            if (j > 0) {
+                mbar_wait(pv_done, (j - 1) & 1);
+                tc_fence_after();
+                if (any_need) {
+                    uint32_t o[32];
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {
+                        tmem_ld_32x32b_x32(t_lane + O_COL + hh * 32, o);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * factor);
+                        tmem_st_32x32b_x32(t_lane + O_COL + hh * 32, o);
+                    }
+                    tmem_st_wait();
+                }
+            }
+            // ---- P row -> smem, K-major SWIZZLE_128B: 16-byte chunk jj of row r sits at position jj ^ (r & 7)
+            {
+                uint8_t* prow = sP + row * 128;
+#pragma unroll
+                for (int ch = 0; ch < 16; ++ch) {
+                    const int region = ch >> 3, jj = ch & 7;
+                    // 16-byte chunk ch = columns [8 ch, 8 ch + 8) = packed words [4 ch, 4 ch + 4)
+                    uint4 v = make_uint4(pk[ch >> 2][(ch & 3) * 4 + 0], pk[ch >> 2][(ch & 3) * 4 + 1], pk[ch >> 2][(ch & 3) * 4 + 2],
+                                         pk[ch >> 2][(ch & 3) * 4 + 3]);
+                    *reinterpret_cast<uint4*>(prow + region * TILE_BYTES + ((jj ^ (row & 7)) << 4)) = v;
+                }
+            }
+            fence_proxy_async_smem();
+            tc_fence_before();
+            mbar_arrive(p_full);
+        }
+        // ---- epilogue: O / l -> f16 -> global (each thread owns one 128-byte row segment)
+        mbar_wait(pv_done, (n_kv - 1) & 1);
+        tc_fence_after();
+        const float inv = 1.0f / l_sum;
+        const int qrow = q0 + row;
+        __half* orow = out + (static_cast<size_t>(b) * T + qrow) * D + h * HD;
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+            uint32_t o[32];
+            tmem_ld_32x32b_x32(t_lane + O_COL + hh * 32, o);
+            tmem_ld_wait();
+            if (qrow < T) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 8) {
+                    uint4 v;
+                    __half2 a0 = __floats2half2_rn(__uint_as_float(o[i + 0]) * inv, __uint_as_float(o[i + 1]) * inv);
+                    __half2 a1 = __floats2half2_rn(__uint_as_float(o[i + 2]) * inv, __uint_as_float(o[i + 3]) * inv);
+                    __half2 a2 = __floats2half2_rn(__uint_as_float(o[i + 4]) * inv, __uint_as_float(o[i + 5]) * inv);
+                    __half2 a3 = __floats2half2_rn(__uint_as_float(o[i + 6]) * inv, __uint_as_float(o[i + 7]) * inv);
+                    v.x = *reinterpret_cast<uint32_t*>(&a0); v.y = *reinterpret_cast<uint32_t*>(&a1);
+                    v.z = *reinterpret_cast<uint32_t*>(&a2); v.w = *reinterpret_cast<uint32_t*>(&a3);
+                    *reinterpret_cast<uint4*>(orow + hh * 32 + i) = v;
+                }
+            }
+        }
+        tc_fence_before();
+    }
+
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled get_encode_fn() {
+    static PFN_encodeTiled fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_encodeTiled>(f);
+    });
+    return fn;
+}
+
+}  // namespace
+
+cudaError_t attention_f16_tcgen05(const __half* qkv, __half* out, int B, int T, int H, cudaStream_t st) {
+    if (B <= 0 || T <= 0 || H <= 0) return cudaErrorInvalidValue;
+    const int D = H * HD;
+    PFN_encodeTiled enc = get_encode_fn();
+    if (!enc) return cudaErrorInvalidValue;
+    // qkv viewed as [B][T][3D] f16: rows >= T of a window are out of bounds for the map (zero fill), never the next window
+    CUtensorMap tm;
+    cuuint64_t dims[3] = {static_cast<cuuint64_t>(3 * D), static_cast<cuuint64_t>(T), static_cast<cuuint64_t>(B)};
+    cuuint64_t strides[2] = {static_cast<cuuint64_t>(3 * D) * sizeof(__half), static_cast<cuuint64_t>(T) * 3 * D * sizeof(__half)};
+    cuuint32_t box[3] = {HD, BKV, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    if (enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<__half*>(qkv), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return cudaErrorInvalidValue;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    dim3 grid((T + BQ - 1) / BQ, H, B);
+    attention_tc_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(tm, out, T, D);
+    return cudaGetLastError();
+}
+
+}  // namespace q2w

@@ -238,7 +238,7 @@ int forward_from_a1(q2w_state* s, int Bm, int w0) {
         // softmax(Q K^T) V per head   (:2080-2106)
         {
             ProfScope ps(s, PC_ATTN, 4.0 * Bm * static_cast<double>(T) * T * D, 8.0 * M * D);
-            CKL(attention_f16(s->qkv, s->att, Bm, T, H, s->stream));
+            CKL(attention_f16_tcgen05(s->qkv, s->att, Bm, T, H, s->stream));
         }
         // out-proj + bias + residual   (:2112-2120)
         if ((rc = weight_gemm(s, s->att, D, L.o_w.d, m->wtype_dev, M, D, D, static_cast<const float*>(L.o_b.d), s->x, D,
@@ -775,6 +775,11 @@ int q2w_op_pool_layernorm(const float* x, const float* gamma, const float* beta,
 }
 
 int q2w_op_attention(const void* qkv, void* out, int B, int T, int H, void* stream) {
+    CKL(attention_f16_tcgen05(static_cast<const __half*>(qkv), static_cast<__half*>(out), B, T, H, static_cast<cudaStream_t>(stream)));
+    return Q2W_OK;
+}
+
+int q2w_op_attention_legacy_mma(const void* qkv, void* out, int B, int T, int H, void* stream) {
     CKL(attention_f16(static_cast<const __half*>(qkv), static_cast<__half*>(out), B, T, H, static_cast<cudaStream_t>(stream)));
     return Q2W_OK;
 }

@@ -5,12 +5,13 @@
 // mul_mats produced by ggml_conv_1d_ph :1922/:1927) together with the elementwise nodes that follow
 // them (ggml_add bias, ggml_scale, ggml_gelu, residual ggml_add, positional-embedding add).
 //
-// Design (one CTA per SM, 192 threads):
+// Design (one CTA per SM, 320 threads):
 //   warp 0   : TMA producer   -- cp.async.bulk.tensor 2D loads of A (128 x 64) and W (256 x 64) f16 tiles,
 //                                SWIZZLE_128B, 4-stage mbarrier ring
 //   warp 1   : MMA issuer     -- one elected thread issues tcgen05.mma.cta_group::1.kind::f16 (M128 N256 K16),
 //                                accumulators live in TMEM, double-buffered (2 x 256 columns)
-//   warps 2-5: epilogue       -- tcgen05.ld 32x32b.x32 -> registers -> bias / scale / GELU / residual / pos -> global
+//   warps 2-9: epilogue       -- two warps per TMEM lane quadrant (128 columns each): tcgen05.ld 32x32b.x32 -> registers ->
+//                                smem transpose -> bias / scale / GELU / residual / pos -> coalesced global stores
 // The epilogue of tile i overlaps the main loop of tile i+1 through the two TMEM accumulator stages.
 // M, N, K tails are handled by TMA zero-fill on the load side and predication on the store side.
 #include "ops.h"
@@ -28,8 +29,10 @@ constexpr int STAGES = 4;
 constexpr int A_BYTES = BM * BK * 2;   // 16 KB
 constexpr int B_BYTES = BN * BK * 2;   // 32 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-constexpr int NUM_THREADS = 192;
+constexpr int EPI_WARPS = 8;
+constexpr int EPI_STAGE_BYTES = EPI_WARPS * 32 * 33 * 4;  // per-epilogue-warp 32 x 33 f32 transpose buffers
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_STAGE_BYTES;
+constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;
 constexpr int TMEM_COLS = 512;
 constexpr int UMMA_K = 16;
 
@@ -79,7 +82,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&tfull_bar[s], 1);
-            mbar_init(&tempty_bar[s], 4);  // one arrive per epilogue warp
+            mbar_init(&tempty_bar[s], EPI_WARPS);  // one arrive per epilogue warp
         }
         fence_mbar_init();
     }
@@ -144,91 +147,103 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
         __syncwarp();
     } else {
-        // ------------------------------------------------------------ epilogue (warps 2..5)
-        const int q = warp & 3;            // TMEM lane quadrant this warp may access
-        const int row_in_tile = q * 32 + lane;
+        // ------------------------------------------------------------ epilogue (warps 2..9)
+        // TMEM -> registers (lane = row) -> per-warp smem transpose (pitch 33, conflict-free both ways) -> lane = column:
+        // every global access below is a contiguous row segment (128 B per warp instruction), bias / residual / positional
+        // reads included, and the residual rows of chunk c+1 are in flight while chunk c is processed.
+        // (Round-1 profile: row-per-lane stores cost 32 sectors per request and made the K=1280 GEMMs epilogue-bound.)
+        const int q = warp & 3;                    // TMEM lane quadrant this warp may access
+        const int chalf = (warp - 2) >> 2;         // which 128-column half of the tile
+        float* stg = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256) + (warp - 2) * (32 * 33);
         int acc = 0;
         uint32_t acc_phase = 0;
+        constexpr bool F16OUT = (EPI == EPI_BIAS_F16 || EPI == EPI_BIAS_GELU_F16);
+        constexpr bool HAS_ADD = (EPI == EPI_BIAS_RESID_F32 || EPI == EPI_BIAS_GELU_POS_F32);
+        constexpr int CHUNKS = BN / 32 / 2;        // chunks per warp
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const int m0 = (tile / p.n_tiles) * BM;
-            const int n0 = (tile % p.n_tiles) * BN;
-            const int m = m0 + row_in_tile;
+            const int m0 = (tile / p.n_tiles) * BM + q * 32;
+            const int n0 = (tile % p.n_tiles) * BN + chalf * (BN / 2);
+            const int rows = min(32, p.M - m0);       // valid rows of this warp's quadrant (may be <= 0)
+            int pm = 0;
+            if constexpr (EPI == EPI_BIAS_GELU_POS_F32) pm = m0 % p.pos_period;
+            // rows of the residual / positional operand for one 32-column chunk: 32 independent coalesced loads per lane
+            auto load_add = [&](int n, float (&add)[32]) {
+                const int nc = n + lane;
+                const bool ok = nc < p.N;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    add[i] = 0.f;
+                    if (i < rows && ok) {
+                        if constexpr (EPI == EPI_BIAS_RESID_F32) add[i] = p.resid[static_cast<size_t>(m0 + i) * p.ldo + nc];
+                        if constexpr (EPI == EPI_BIAS_GELU_POS_F32) {
+                            int pr = pm + i;
+                            if (pr >= p.pos_period) pr -= p.pos_period;
+                            add[i] = __ldg(p.pos + static_cast<size_t>(pr) * p.N + nc);
+                        }
+                    }
+                }
+            };
+            float add[32];
+            if constexpr (HAS_ADD) {
+                if (n0 < p.N) load_add(n0, add);      // does not depend on the accumulator: issued before the wait
+            }
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
-            const uint32_t t_row = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
-            const float* pos_row = nullptr;
-            if constexpr (EPI == EPI_BIAS_GELU_POS_F32) {
-                pos_row = p.pos + static_cast<size_t>(m % p.pos_period) * p.N;
-            }
+            const uint32_t t_row = tmem_base + acc * BN + chalf * (BN / 2) + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
+            for (int c = 0; c < CHUNKS; ++c) {
                 const int n = n0 + c * 32;
                 if (n >= p.N) break;  // warp-uniform
                 uint32_t r[32];
                 tmem_ld_32x32b_x32(t_row + c * 32, r);
                 tmem_ld_wait();
-                if (m < p.M) {
 #pragma unroll
-                    for (int g = 0; g < 4; ++g) {  // 8 columns per group
-                        const int ng = n + g * 8;
-                        if (ng < p.N) {
-                            float v[8];
-                            float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
-                            if (p.bias) {
-                                b0 = __ldg(reinterpret_cast<const float4*>(p.bias + ng));
-                                b1 = __ldg(reinterpret_cast<const float4*>(p.bias + ng + 4));
-                            }
-                            v[0] = __uint_as_float(r[g * 8 + 0]) + b0.x;
-                            v[1] = __uint_as_float(r[g * 8 + 1]) + b0.y;
-                            v[2] = __uint_as_float(r[g * 8 + 2]) + b0.z;
-                            v[3] = __uint_as_float(r[g * 8 + 3]) + b0.w;
-                            v[4] = __uint_as_float(r[g * 8 + 4]) + b1.x;
-                            v[5] = __uint_as_float(r[g * 8 + 5]) + b1.y;
-                            v[6] = __uint_as_float(r[g * 8 + 6]) + b1.z;
-                            v[7] = __uint_as_float(r[g * 8 + 7]) + b1.w;
-                            if constexpr (EPI == EPI_BIAS_F16) {
-                                if (ng < p.scale_cols) {
-#pragma unroll
-                                    for (int i = 0; i < 8; ++i) v[i] *= p.scale;
-                                }
-                            }
-                            if constexpr (EPI == EPI_BIAS_GELU_F16 || EPI == EPI_BIAS_GELU_POS_F32) {
-#pragma unroll
-                                for (int i = 0; i < 8; ++i) v[i] = gelu_tanh(v[i]);
-                            }
-                            if constexpr (EPI == EPI_BIAS_F16 || EPI == EPI_BIAS_GELU_F16) {
-                                __half* o = reinterpret_cast<__half*>(p.out) + static_cast<size_t>(m) * p.ldo + ng;
-                                uint4 pk;
-                                __half2 h0 = __floats2half2_rn(v[0], v[1]);
-                                __half2 h1 = __floats2half2_rn(v[2], v[3]);
-                                __half2 h2 = __floats2half2_rn(v[4], v[5]);
-                                __half2 h3 = __floats2half2_rn(v[6], v[7]);
-                                pk.x = *reinterpret_cast<uint32_t*>(&h0);
-                                pk.y = *reinterpret_cast<uint32_t*>(&h1);
-                                pk.z = *reinterpret_cast<uint32_t*>(&h2);
-                                pk.w = *reinterpret_cast<uint32_t*>(&h3);
-                                *reinterpret_cast<uint4*>(o) = pk;
-                            } else {
-                                float* o = reinterpret_cast<float*>(p.out) + static_cast<size_t>(m) * p.ldo + ng;
-                                if constexpr (EPI == EPI_BIAS_RESID_F32) {
-                                    const float* rs = p.resid + static_cast<size_t>(m) * p.ldo + ng;
-                                    const float4 r0 = *reinterpret_cast<const float4*>(rs);
-                                    const float4 r1 = *reinterpret_cast<const float4*>(rs + 4);
-                                    v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w;
-                                    v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
-                                }
-                                if constexpr (EPI == EPI_BIAS_GELU_POS_F32) {
-                                    const float4 p0 = __ldg(reinterpret_cast<const float4*>(pos_row + ng));
-                                    const float4 p1 = __ldg(reinterpret_cast<const float4*>(pos_row + ng + 4));
-                                    v[0] += p0.x; v[1] += p0.y; v[2] += p0.z; v[3] += p0.w;
-                                    v[4] += p1.x; v[5] += p1.y; v[6] += p1.z; v[7] += p1.w;
-                                }
-                                *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
-                                *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
-                            }
+                for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = __uint_as_float(r[j]);
+                __syncwarp();
+                if constexpr (F16OUT) {
+                    // two rows per instruction: lanes 0-15 -> row rr, lanes 16-31 -> row rr+1, two columns per lane
+                    const int half = lane >> 4, l2 = (lane & 15) * 2;
+                    const int nc = n + l2;
+                    const bool col_ok = nc < p.N;     // N % 8 == 0 -> the pair is valid together
+                    float b0 = 0.f, b1 = 0.f;
+                    if (p.bias && col_ok) { b0 = __ldg(p.bias + nc); b1 = __ldg(p.bias + nc + 1); }
+                    float sc = 1.0f;
+                    if constexpr (EPI == EPI_BIAS_F16) sc = (nc < p.scale_cols) ? p.scale : 1.0f;
+                    __half* obase = reinterpret_cast<__half*>(p.out) + static_cast<size_t>(m0) * p.ldo + nc;
+#pragma unroll 4
+                    for (int rr = 0; rr < 32; rr += 2) {
+                        const int row = rr + half;
+                        float v0 = stg[row * 33 + l2] + b0;
+                        float v1 = stg[row * 33 + l2 + 1] + b1;
+                        if constexpr (EPI == EPI_BIAS_F16) { v0 *= sc; v1 *= sc; }
+                        if constexpr (EPI == EPI_BIAS_GELU_F16) { v0 = gelu_tanh(v0); v1 = gelu_tanh(v1); }
+                        if (row < rows && col_ok) {
+                            __half2 h = __floats2half2_rn(v0, v1);
+                            *reinterpret_cast<__half2*>(obase + static_cast<size_t>(row) * p.ldo) = h;
                         }
                     }
+                } else {
+                    float addn[32];
+                    if constexpr (HAS_ADD) {
+                        if (c + 1 < CHUNKS && n + 32 < p.N) load_add(n + 32, addn);   // prefetch the next chunk's rows
+                    }
+                    const int nc = n + lane;
+                    const bool col_ok = nc < p.N;
+                    const float bv = (p.bias && col_ok) ? __ldg(p.bias + nc) : 0.f;
+                    float* obase = reinterpret_cast<float*>(p.out) + static_cast<size_t>(m0) * p.ldo + nc;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        float v = stg[i * 33 + lane] + bv;
+                        if constexpr (EPI == EPI_BIAS_GELU_POS_F32) v = gelu_tanh(v);
+                        if constexpr (HAS_ADD) v += add[i];
+                        if (i < rows && col_ok) obase[static_cast<size_t>(i) * p.ldo] = v;
+                    }
+                    if constexpr (HAS_ADD) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) add[i] = addn[i];
+                    }
                 }
+                __syncwarp();  // the staging buffer is rewritten by the next chunk
             }
             // all TMEM reads of this warp are complete (wait::ld above): hand the accumulator back
             tc_fence_before();

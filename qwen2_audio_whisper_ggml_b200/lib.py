@@ -67,6 +67,7 @@ _SIGS = {
     "q2w_op_layernorm": (_i, [_vp, _vp, _vp, _vp, _i, _i, _f, _vp]),
     "q2w_op_pool_layernorm": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp]),
     "q2w_op_attention": (_i, [_vp, _vp, _i, _i, _i, _vp]),
+    "q2w_op_attention_legacy_mma": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "q2w_op_dequant": (_i, [_vp, _i, _vp, _sz, _i, _vp]),
     "q2w_op_conv2_im2col": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "q2w_op_mel": (_i, [_vp, _i, _vp, _sz, _vp, _i, _i, _i, _vp, _i, _vp, _i, _vp]),
