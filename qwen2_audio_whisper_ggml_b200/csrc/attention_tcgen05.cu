@@ -136,7 +136,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm, __half* __restrict__
             const uint64_t p_desc = make_sw128_kmajor_desc(smem_u32(sP));
             const uint64_t v_desc = make_sw128_mnmajor_desc(smem_u32(sV));
             mbar_wait(q_full, 0);
-            for (int j = 0; j < n_kv; ++j) {
+            // software pipeline: S_{j+1} = Q K_{j+1}^T is issued BEFORE waiting for P_j, so it runs under softmax_j's exp phase
+            // (the single S buffer is free as soon as softmax_j has pulled its row into registers: s_empty).  Round-1 timeline:
+            // the in-order issue QK_j, PV_j, QK_{j+1} serialised softmax_{j+1} behind softmax_j + PV_j (4400 cycles per tile).
+            auto issue_qk = [&](int j) {
                 mbar_wait(k_full, j & 1);
                 if (j > 0) mbar_wait(s_empty, (j - 1) & 1);
                 tc_fence_after();
@@ -145,6 +148,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm, __half* __restrict__
                     umma_f16_ss(tmem_base + S_COL, q_desc + 2 * k, k_desc + 2 * k, idesc_qk, k != 0);
                 umma_commit(s_full);
                 umma_commit(k_empty);
+            };
+            issue_qk(0);
+            for (int j = 0; j < n_kv; ++j) {
+                if (j + 1 < n_kv) issue_qk(j + 1);
                 mbar_wait(p_full, j & 1);
                 mbar_wait(v_full, j & 1);
                 tc_fence_after();
@@ -186,14 +193,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm, __half* __restrict__
                     for (int i = 0; i < 32; ++i)
                         if (c4 * 32 + i >= valid) s[c4][i] = __float_as_uint(-INFINITY);
             }
+            {
+                float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-            for (int c4 = 0; c4 < 4; ++c4)
+                for (int c4 = 0; c4 < 4; ++c4)
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const float v = __uint_as_float(s[c4][i]) * LOG2E;
-                    s[c4][i] = __float_as_uint(v);
-                    mx = fmaxf(mx, v);
-                }
+                    for (int i = 0; i < 32; ++i) m4[c4] = fmaxf(m4[c4], __uint_as_float(s[c4][i]));   // 4 independent chains
+                mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+            }
+            mx *= LOG2E;   // log2 domain; p = ex2(s * log2e - m) is one FFMA + one MUFU per element
             // ---- lazy rescale decision (warp-uniform because tcgen05.ld/st are warp-collective)
             float factor = 1.0f;
             bool need = false;
@@ -207,19 +215,19 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm, __half* __restrict__
             }
             const bool any_need = __any_sync(0xffffffffu, need);
             // ---- probabilities
-            float rs = 0.f;
+            float rs4[4] = {0.f, 0.f, 0.f, 0.f};
             uint32_t pk[4][16];
 #pragma unroll
             for (int c4 = 0; c4 < 4; ++c4)
 #pragma unroll
                 for (int i = 0; i < 32; i += 2) {
-                    const float p0 = ex2(__uint_as_float(s[c4][i]) - m_used);
-                    const float p1 = ex2(__uint_as_float(s[c4][i + 1]) - m_used);
-                    rs += p0 + p1;
+                    const float p0 = ex2(fmaf(__uint_as_float(s[c4][i]), LOG2E, -m_used));
+                    const float p1 = ex2(fmaf(__uint_as_float(s[c4][i + 1]), LOG2E, -m_used));
+                    rs4[c4] += p0 + p1;
                     __half2 hh = __floats2half2_rn(p0, p1);
                     pk[c4][i >> 1] = *reinterpret_cast<uint32_t*>(&hh);
                 }
-            l_sum += rs;
+            l_sum += (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]);
             // ---- P and V buffers free, O_{j-1} accumulated
             if (j > 0) {
                 mbar_wait(pv_done, (j - 1) & 1);
