@@ -165,6 +165,8 @@ def main():
         raise SystemExit("bench.py: no CUDA device (there is no CPU fallback for the product arm; use --impl reference)")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        # stdout carries exactly one JSON line: NCCL's version / debug banner (NCCL_DEBUG is set on the GPU boxes) goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     lib = L.load_library()
     api.log_set(lambda lvl, txt: None)
