@@ -11,10 +11,10 @@
 //   warp 0      TMA producer: Q once, then K_j / V_j tiles (128 x 64 f16, SWIZZLE_128B) through a 3-D tensor map over
 //               qkv[B][T][3D] -- rows past T are out of bounds for the map and arrive as zeros, never as the next window
 //   warp 1      MMA issuer:  S = Q K_j^T   tcgen05.mma kind::f16  M128 N128 K16 x4   (A, B K-major)          -> TMEM cols [0,128)
-//                            O += P_j V_j  tcgen05.mma kind::f16  M128 N64  K16 x8   (A = P K-major from smem,
+//                            O += P_j V_j  tcgen05.mma kind::f16  M128 N64  K16 x8   (A = P read from TMEM cols [192,256),
 //                                                                                      B = V MN-major as loaded) -> TMEM cols [128,192)
 //   warps 4-7   softmax, one thread per query row: tcgen05.ld the S row (single pass, 128 registers), mask the ragged last
-//               tile, running max / sum in the log2 domain, ex2, pack to F16, write the P row into the swizzled smem tile.
+//               tile, running max / sum in the log2 domain, ex2, pack to F16, tcgen05.st the P row back into TMEM.
 //               O stays in TMEM for the whole KV loop; it is rescaled (tcgen05.ld -> mul -> tcgen05.st) only when the
 //               running max grew by more than 2^8 since the last rescale -- the stale max is exact algebra, it only bounds
 //               the magnitude of P (<= 256 in F16), and the final division by the row sum uses the same reference point.
@@ -31,11 +31,10 @@ namespace {
 constexpr int HD = 64, BQ = 128, BKV = 128;
 constexpr int THREADS = 256;
 constexpr int TILE_BYTES = 128 * 128;           // 128 rows x 64 f16 = 16 KB
-constexpr int P_BYTES = 2 * TILE_BYTES;         // 128 x 128 f16 as two K-major 64-column chunks
-constexpr int SMEM_DATA = 3 * TILE_BYTES + P_BYTES;   // Q, K, V, P = 80 KB
+constexpr int SMEM_DATA = 3 * TILE_BYTES;       // Q, K, V = 48 KB (P never touches shared memory)
 constexpr int SMEM_BYTES = SMEM_DATA + 1024 /*align*/ + 128 /*barriers*/;
 constexpr int TMEM_COLS = 256;
-constexpr int S_COL = 0, O_COL = 128;
+constexpr int S_COL = 0, O_COL = 128, P_COL = 192;   // S f32 [0,128) | O f32 [128,192) | P f16x2 [192,256)
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float RESCALE_THRESHOLD = 8.0f;       // log2 units
 
@@ -67,6 +66,15 @@ __device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_
         "r"(r[30]), "r"(r[31])
         : "memory");
 }
+// D[tmem] (+)= A[tmem] * B[smem desc]: the A operand (M = 128 rows in lanes, K packed two f16 per column) comes from TMEM
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 __global__ void __launch_bounds__(THREADS, 2)
@@ -76,7 +84,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm, __half* __restrict__
     uint8_t* sQ = smem;
     uint8_t* sK = smem + TILE_BYTES;
     uint8_t* sV = smem + 2 * TILE_BYTES;
-    uint8_t* sP = smem + 3 * TILE_BYTES;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SMEM_DATA);
     uint64_t* q_full = bars + 0;
     uint64_t* k_full = bars + 1;
@@ -133,7 +140,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm, __half* __restrict__
             constexpr uint32_t idesc_pv = make_idesc_f16(BQ, HD, 0, 1);     // B = V is MN-major
             const uint64_t q_desc = make_sw128_kmajor_desc(smem_u32(sQ));
             const uint64_t k_desc = make_sw128_kmajor_desc(smem_u32(sK));
-            const uint64_t p_desc = make_sw128_kmajor_desc(smem_u32(sP));
             const uint64_t v_desc = make_sw128_mnmajor_desc(smem_u32(sV));
             mbar_wait(q_full, 0);
             // software pipeline: S_{j+1} = Q K_{j+1}^T is issued BEFORE waiting for P_j, so it runs under softmax_j's exp phase
@@ -157,11 +163,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm, __half* __restrict__
                 tc_fence_after();
 #pragma unroll
                 for (int k = 0; k < BKV / 16; ++k) {
-                    // P: two 64-column K-major chunks of 16 KB, 32 B per 16-element K step inside a chunk
-                    const uint64_t pa = p_desc + static_cast<uint64_t>((k >> 2) * (TILE_BYTES >> 4) + (k & 3) * 2);
+                    // P is the A operand straight from TMEM: lane = query row, 16 f16 (one K step) = 8 packed 32-bit columns
                     // V: 16 K rows (kv) per step = 2 KB
                     const uint64_t vb = v_desc + static_cast<uint64_t>(k * (2048 >> 4));
-                    umma_f16_ss(tmem_base + O_COL, pa, vb, idesc_pv, (j | k) != 0);
+                    umma_f16_ts(tmem_base + O_COL, tmem_base + P_COL + k * 8, vb, idesc_pv, (j | k) != 0);
                 }
                 umma_commit(pv_done);
             }
@@ -245,19 +250,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm, __half* __restrict__
                     tmem_st_wait();
                 }
             }
-            // ---- P row -> smem, K-major SWIZZLE_128B: 16-byte chunk jj of row r sits at position jj ^ (r & 7)
-            {
-                uint8_t* prow = sP + row * 128;
-#pragma unroll
-                for (int ch = 0; ch < 16; ++ch) {
-                    const int region = ch >> 3, jj = ch & 7;
-                    // 16-byte chunk ch = columns [8 ch, 8 ch + 8) = packed words [4 ch, 4 ch + 4)
-                    uint4 v = make_uint4(pk[ch >> 2][(ch & 3) * 4 + 0], pk[ch >> 2][(ch & 3) * 4 + 1], pk[ch >> 2][(ch & 3) * 4 + 2],
-                                         pk[ch >> 2][(ch & 3) * 4 + 3]);
-                    *reinterpret_cast<uint4*>(prow + region * TILE_BYTES + ((jj ^ (row & 7)) << 4)) = v;
-                }
-            }
-            fence_proxy_async_smem();
+            // ---- P row -> TMEM columns [192,256) (two f16 per 32-bit column): no shared memory, no proxy fence
+            tmem_st_32x32b_x32(t_lane + P_COL, *reinterpret_cast<uint32_t (*)[32]>(&pk[0][0]));
+            tmem_st_32x32b_x32(t_lane + P_COL + 32, *reinterpret_cast<uint32_t (*)[32]>(&pk[2][0]));
+            tmem_st_wait();
             tc_fence_before();
             mbar_arrive(p_full);
         }
