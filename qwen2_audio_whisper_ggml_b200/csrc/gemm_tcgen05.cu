@@ -1,19 +1,24 @@
-// gemm_tcgen05.cu -- persistent, warp-specialised F16 x F16 -> F32 GEMM for sm_100a.
+// gemm_tcgen05.cu -- persistent, warp-specialised F16 x F16 -> F32 GEMM for sm_100a on CTA PAIRS (cta_group::2).
 //
 // Replaces, on the encoder path, every weight ggml_mul_mat of the reference graph
 // (src/qwen2-whisper.cpp:2029-2046 Q/K/V, :2112 out-proj, :2137 fc1, :2147 fc2, and the conv stem
 // mul_mats produced by ggml_conv_1d_ph :1922/:1927) together with the elementwise nodes that follow
 // them (ggml_add bias, ggml_scale, ggml_gelu, residual ggml_add, positional-embedding add).
 //
-// Design (one CTA per SM, 320 threads):
-//   warp 0   : TMA producer   -- cp.async.bulk.tensor 2D loads of A (128 x 64) and W (256 x 64) f16 tiles,
-//                                SWIZZLE_128B, 4-stage mbarrier ring
-//   warp 1   : MMA issuer     -- one elected thread issues tcgen05.mma.cta_group::1.kind::f16 (M128 N256 K16),
-//                                accumulators live in TMEM, double-buffered (2 x 256 columns)
-//   warps 2-9: epilogue       -- two warps per TMEM lane quadrant (128 columns each): tcgen05.ld 32x32b.x32 -> registers ->
-//                                smem transpose -> bias / scale / GELU / residual / pos -> coalesced global stores
-// The epilogue of tile i overlaps the main loop of tile i+1 through the two TMEM accumulator stages.
-// M, N, K tails are handled by TMA zero-fill on the load side and predication on the store side.
+// Design (cluster of 2 CTAs = one 256 x 256 output tile at a time, one cluster per SM pair, 320 threads per CTA):
+//   warp 0    TMA producer (both CTAs): its own 128 x 64 slice of A and its own 128-row half of the 256 x 64 W tile
+//             (cp.async.bulk.tensor.2d.cta_group::2, SWIZZLE_128B), completion bytes of BOTH CTAs land on the leader's
+//             full barrier.  4-stage ring, 32 KB per stage per CTA -- each CTA fetches 1/3 less from L2 than a 128 x 256
+//             single-CTA tile would, and the freed shared memory pays for the epilogue buffers below.
+//   warp 1    MMA issuer (leader CTA only): tcgen05.mma.cta_group::2.kind::f16, M256 N256 K16; accumulators live in TMEM
+//             (128 lanes x 256 columns per CTA), double-buffered; tcgen05.commit ... multicast::cluster releases the smem
+//             stage / publishes the accumulator in both CTAs.
+//   warps 2-9 epilogue, two per TMEM lane quadrant.  Everything stays in the "lane = output row" domain the accumulator
+//             arrives in: tcgen05.ld -> bias (broadcast loads) / scale / GELU in registers -> residual added from a tile the
+//             warp TMA-loaded two chunks earlier -> result written in place into the 128B-swizzled smem chunk -> one TMA
+//             store per 32-row chunk.  No per-element global address arithmetic, no predication: M/N tails are clipped by
+//             the TMA unit on store and zero-filled on load.  (Round-1 profiles: the per-element LDG/STG epilogue spent
+//             ~45 % of its issue slots on 64-bit address math and kept the K = 1280 GEMMs at 45-55 % tensor-pipe activity.)
 #include "ops.h"
 #include "ptx.cuh"
 
@@ -24,14 +29,19 @@ namespace q2w {
 
 namespace {
 
-constexpr int BM = 128, BN = 256, BK = 64;
+constexpr int BM = 128;            // rows per CTA (256 per pair)
+constexpr int BN = 256;            // columns per pair tile; each CTA stages BN/2 rows of W
+constexpr int BK = 64;
 constexpr int STAGES = 4;
-constexpr int A_BYTES = BM * BK * 2;   // 16 KB
-constexpr int B_BYTES = BN * BK * 2;   // 32 KB
+constexpr int A_BYTES = BM * BK * 2;          // 16 KB
+constexpr int B_BYTES = (BN / 2) * BK * 2;    // 16 KB (this CTA's half of W)
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int EPI_WARPS = 8;
-constexpr int EPI_STAGE_BYTES = EPI_WARPS * 32 * 33 * 4;  // per-epilogue-warp 32 x 33 f32 transpose buffers
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_STAGE_BYTES;
+constexpr int EPI_BUFS = 3;                   // per-warp rotation: load (2 chunks ahead) / compute in place / store draining
+constexpr int CHUNK_BYTES = 32 * 128;         // 32 rows x 128 B (32 f32 or 64 f16 columns)
+constexpr int EPI_BYTES = EPI_WARPS * EPI_BUFS * CHUNK_BYTES;   // 96 KB
+constexpr int BAR_BYTES = 512;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024 /*align slack*/;
 constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;
 constexpr int TMEM_COLS = 512;
 constexpr int UMMA_K = 16;
@@ -39,14 +49,11 @@ constexpr int UMMA_K = 16;
 struct KParams {
     int M, N, K;
     const float* bias;
-    void* out;
-    int ldo;
-    const float* resid;
     const float* pos;
     int pos_period;
     int scale_cols;
     float scale;
-    int m_tiles, n_tiles;
+    int m_tiles, n_tiles;   // in units of 256 x 256
 };
 
 __device__ __forceinline__ float gelu_tanh(float x) {
@@ -57,72 +64,84 @@ __device__ __forceinline__ float gelu_tanh(float x) {
 }
 
 template <int EPI>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const KParams p) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+            const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR, const KParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
-    uint64_t* full_bar = bars;                    // [STAGES]
-    uint64_t* empty_bar = bars + STAGES;          // [STAGES]
-    uint64_t* tfull_bar = bars + 2 * STAGES;      // [2]
-    uint64_t* tempty_bar = bars + 2 * STAGES + 2; // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+    uint8_t* epi_smem = smem + STAGES * STAGE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(epi_smem + EPI_BYTES);
+    uint64_t* full_bar = bars;                       // [STAGES]  used in the leader CTA only
+    uint64_t* empty_bar = bars + STAGES;             // [STAGES]  one per CTA, released by the leader's multicast commit
+    uint64_t* tfull_bar = bars + 2 * STAGES;         // [2]       accumulator ready, multicast to both CTAs
+    uint64_t* tempty_bar = bars + 2 * STAGES + 2;    // [2]       leader only: 2 x EPI_WARPS arrivals
+    uint64_t* rbar = bars + 2 * STAGES + 4;          // [EPI_WARPS][EPI_BUFS] residual chunk landed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rbar + EPI_WARPS * EPI_BUFS);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    const uint32_t cta_rank = cluster_ctarank();
+    const bool leader = cta_rank == 0;
+    const int cluster_id = blockIdx.x >> 1;
+    const int num_clusters = gridDim.x >> 1;
     const int num_tiles = p.m_tiles * p.n_tiles;
     const int nkb = (p.K + BK - 1) / BK;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
+        tma_prefetch_desc(&tmO);
+        if constexpr (EPI == EPI_BIAS_RESID_F32) tma_prefetch_desc(&tmR);
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&tfull_bar[s], 1);
-            mbar_init(&tempty_bar[s], EPI_WARPS);  // one arrive per epilogue warp
+            mbar_init(&tempty_bar[s], 2 * EPI_WARPS);
         }
+        for (int i = 0; i < EPI_WARPS * EPI_BUFS; ++i) mbar_init(&rbar[i], 1);
         fence_mbar_init();
     }
     if (warp == 1) {
-        tmem_alloc(tmem_slot, TMEM_COLS);
-        tmem_relinquish();
+        tmem_alloc_cta2(tmem_slot, TMEM_COLS);
+        tmem_relinquish_cta2();
     }
     tc_fence_before();
-    __syncthreads();
+    cluster_sync_all();          // barrier inits of both CTAs visible before any remote arrive / multicast
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ------------------------------------------------------------ TMA producer
+        // ------------------------------------------------------------ TMA producer (both CTAs)
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int m0 = (tile / p.n_tiles) * BM;
-                const int n0 = (tile % p.n_tiles) * BN;
+            for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+                const int m0 = (tile / p.n_tiles) * (2 * BM) + static_cast<int>(cta_rank) * BM;
+                const int n0 = (tile % p.n_tiles) * BN + static_cast<int>(cta_rank) * (BN / 2);
                 for (int kb = 0; kb < nkb; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sA = smem + stage * STAGE_BYTES;
                     uint8_t* sB = sA + A_BYTES;
-                    mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
-                    tma_load_2d(sA, &tmA, &full_bar[stage], kb * BK, m0);
-                    tma_load_2d(sB, &tmB, &full_bar[stage], kb * BK, n0);
+                    if (leader) mbar_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);   // bytes of both CTAs
+                    const uint32_t full_leader = smem_u32(&full_bar[stage]) & kPeerBitMask;
+                    tma_load_2d_cta2(sA, &tmA, full_leader, kb * BK, m0);
+                    tma_load_2d_cta2(sB, &tmB, full_leader, kb * BK, n0);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
+        __syncwarp();   // reconverge before the (aligned) cluster barrier below
     } else if (warp == 1) {
-        // ------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_f16(BM, BN);
+        // ------------------------------------------------------------ MMA issuer (leader CTA)
+        if (leader && lane == 0) {
+            constexpr uint32_t idesc = make_idesc_f16(2 * BM, BN);
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BN;
@@ -133,14 +152,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     const uint64_t a_desc = make_sw128_kmajor_desc(a_addr);
                     const uint64_t b_desc = make_sw128_kmajor_desc(a_addr + A_BYTES);
 #pragma unroll
-                    for (int k = 0; k < BK / UMMA_K; ++k) {
-                        // advance 16 elements (32 B) along K inside the 128-byte swizzle row: +2 in (addr >> 4) units
-                        umma_f16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
-                    }
-                    umma_commit(&empty_bar[stage]);  // frees this smem stage once the MMAs above have read it
+                    for (int k = 0; k < BK / UMMA_K; ++k)
+                        umma_f16_ss_cta2(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+                    umma_commit_cta2_mcast(&empty_bar[stage], 0x3);   // both CTAs may refill this stage
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(&tfull_bar[acc]);        // accumulator complete -> epilogue
+                umma_commit_cta2_mcast(&tfull_bar[acc], 0x3);         // accumulator complete in both CTAs
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1;
             }
@@ -148,117 +165,162 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         __syncwarp();
     } else {
         // ------------------------------------------------------------ epilogue (warps 2..9)
-        // TMEM -> registers (lane = row) -> per-warp smem transpose (pitch 33, conflict-free both ways) -> lane = column:
-        // every global access below is a contiguous row segment (128 B per warp instruction), bias / residual / positional
-        // reads included, and the residual rows of chunk c+1 are in flight while chunk c is processed.
-        // (Round-1 profile: row-per-lane stores cost 32 sectors per request and made the K=1280 GEMMs epilogue-bound.)
+        const int ew = warp - 2;
         const int q = warp & 3;                    // TMEM lane quadrant this warp may access
-        const int chalf = (warp - 2) >> 2;         // which 128-column half of the tile
-        float* stg = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256) + (warp - 2) * (32 * 33);
+        const int chalf = ew >> 2;                 // which 128-column half of the tile
+        uint8_t* bufs = epi_smem + ew * (EPI_BUFS * CHUNK_BYTES);
+        uint64_t* my_rbar = rbar + ew * EPI_BUFS;
+        constexpr bool F16OUT = (EPI == EPI_BIAS_F16 || EPI == EPI_BIAS_GELU_F16);
+        constexpr bool RESID = (EPI == EPI_BIAS_RESID_F32);
+        constexpr int CCOLS = F16OUT ? 64 : 32;    // columns per 128-byte chunk row
+        constexpr int CHUNKS = (BN / 2) / CCOLS;   // chunks per warp per tile
+        const uint32_t row_off = static_cast<uint32_t>(lane) * 128;
+        const uint32_t sw = static_cast<uint32_t>(lane & 7);
+
+        // chunk gc (running counter over this warp's whole life) -> coordinates
+        auto chunk_coords = [&](long gc, int& m, int& n) -> bool {
+            const long ti = gc / CHUNKS;
+            const int c = static_cast<int>(gc - ti * CHUNKS);
+            const long tile = cluster_id + ti * num_clusters;
+            if (tile >= num_tiles) return false;
+            m = static_cast<int>(tile / p.n_tiles) * (2 * BM) + static_cast<int>(cta_rank) * BM + q * 32;
+            n = static_cast<int>(tile % p.n_tiles) * BN + chalf * (BN / 2) + c * CCOLS;
+            return true;
+        };
+        auto prefetch_resid = [&](long gc) {   // lane 0 only
+            int m, n;
+            if (!chunk_coords(gc, m, n)) return;
+            const int b = static_cast<int>(gc % EPI_BUFS);
+            mbar_expect_tx(&my_rbar[b], CHUNK_BYTES);
+            tma_load_2d(bufs + b * CHUNK_BYTES, &tmR, &my_rbar[b], n, m);
+        };
+
+        long gc = 0;
+        if constexpr (RESID) {
+            if (lane == 0) { prefetch_resid(0); prefetch_resid(1); }
+        }
         int acc = 0;
         uint32_t acc_phase = 0;
-        constexpr bool F16OUT = (EPI == EPI_BIAS_F16 || EPI == EPI_BIAS_GELU_F16);
-        constexpr bool HAS_ADD = (EPI == EPI_BIAS_RESID_F32 || EPI == EPI_BIAS_GELU_POS_F32);
-        constexpr int CHUNKS = BN / 32 / 2;        // chunks per warp
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const int m0 = (tile / p.n_tiles) * BM + q * 32;
-            const int n0 = (tile % p.n_tiles) * BN + chalf * (BN / 2);
-            const int rows = min(32, p.M - m0);       // valid rows of this warp's quadrant (may be <= 0)
-            int pm = 0;
-            if constexpr (EPI == EPI_BIAS_GELU_POS_F32) pm = m0 % p.pos_period;
-            // rows of the residual / positional operand for one 32-column chunk: 32 independent coalesced loads per lane
-            auto load_add = [&](int n, float (&add)[32]) {
-                const int nc = n + lane;
-                const bool ok = nc < p.N;
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    add[i] = 0.f;
-                    if (i < rows && ok) {
-                        if constexpr (EPI == EPI_BIAS_RESID_F32) add[i] = p.resid[static_cast<size_t>(m0 + i) * p.ldo + nc];
-                        if constexpr (EPI == EPI_BIAS_GELU_POS_F32) {
-                            int pr = pm + i;
-                            if (pr >= p.pos_period) pr -= p.pos_period;
-                            add[i] = __ldg(p.pos + static_cast<size_t>(pr) * p.N + nc);
-                        }
-                    }
-                }
-            };
-            float add[32];
-            if constexpr (HAS_ADD) {
-                if (n0 < p.N) load_add(n0, add);      // does not depend on the accumulator: issued before the wait
-            }
+        for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+            const int m0 = (tile / p.n_tiles) * (2 * BM) + static_cast<int>(cta_rank) * BM + q * 32;
+            const int nbase = (tile % p.n_tiles) * BN + chalf * (BN / 2);
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_row = tmem_base + acc * BN + chalf * (BN / 2) + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll 1
-            for (int c = 0; c < CHUNKS; ++c) {
-                const int n = n0 + c * 32;
-                if (n >= p.N) break;  // warp-uniform
-                uint32_t r[32];
-                tmem_ld_32x32b_x32(t_row + c * 32, r);
-                tmem_ld_wait();
+            for (int c = 0; c < CHUNKS; ++c, ++gc) {
+                const int n = nbase + c * CCOLS;
+                const int b = static_cast<int>(gc % EPI_BUFS);
+                uint8_t* buf = bufs + b * CHUNK_BYTES;
+                float v[CCOLS];
+                {
+                    uint32_t r[32];
+                    tmem_ld_32x32b_x32(t_row + c * CCOLS, r);
+                    if constexpr (F16OUT) {
+                        uint32_t r2[32];
+                        tmem_ld_32x32b_x32(t_row + c * CCOLS + 32, r2);
+                        tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = __uint_as_float(r[j]);
-                __syncwarp();
-                if constexpr (F16OUT) {
-                    // two rows per instruction: lanes 0-15 -> row rr, lanes 16-31 -> row rr+1, two columns per lane
-                    const int half = lane >> 4, l2 = (lane & 15) * 2;
-                    const int nc = n + l2;
-                    const bool col_ok = nc < p.N;     // N % 8 == 0 -> the pair is valid together
-                    float b0 = 0.f, b1 = 0.f;
-                    if (p.bias && col_ok) { b0 = __ldg(p.bias + nc); b1 = __ldg(p.bias + nc + 1); }
-                    float sc = 1.0f;
-                    if constexpr (EPI == EPI_BIAS_F16) sc = (nc < p.scale_cols) ? p.scale : 1.0f;
-                    __half* obase = reinterpret_cast<__half*>(p.out) + static_cast<size_t>(m0) * p.ldo + nc;
-#pragma unroll 4
-                    for (int rr = 0; rr < 32; rr += 2) {
-                        const int row = rr + half;
-                        float v0 = stg[row * 33 + l2] + b0;
-                        float v1 = stg[row * 33 + l2 + 1] + b1;
-                        if constexpr (EPI == EPI_BIAS_F16) { v0 *= sc; v1 *= sc; }
-                        if constexpr (EPI == EPI_BIAS_GELU_F16) { v0 = gelu_tanh(v0); v1 = gelu_tanh(v1); }
-                        if (row < rows && col_ok) {
-                            __half2 h = __floats2half2_rn(v0, v1);
-                            *reinterpret_cast<__half2*>(obase + static_cast<size_t>(row) * p.ldo) = h;
-                        }
-                    }
-                } else {
-                    float addn[32];
-                    if constexpr (HAS_ADD) {
-                        if (c + 1 < CHUNKS && n + 32 < p.N) load_add(n + 32, addn);   // prefetch the next chunk's rows
-                    }
-                    const int nc = n + lane;
-                    const bool col_ok = nc < p.N;
-                    const float bv = (p.bias && col_ok) ? __ldg(p.bias + nc) : 0.f;
-                    float* obase = reinterpret_cast<float*>(p.out) + static_cast<size_t>(m0) * p.ldo + nc;
+                        for (int j = 0; j < 32; ++j) { v[j] = __uint_as_float(r[j]); v[32 + j] = __uint_as_float(r2[j]); }
+                    } else {
+                        tmem_ld_wait();
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        float v = stg[i * 33 + lane] + bv;
-                        if constexpr (EPI == EPI_BIAS_GELU_POS_F32) v = gelu_tanh(v);
-                        if constexpr (HAS_ADD) v += add[i];
-                        if (i < rows && col_ok) obase[static_cast<size_t>(i) * p.ldo] = v;
-                    }
-                    if constexpr (HAS_ADD) {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) add[i] = addn[i];
+                        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
                     }
                 }
-                __syncwarp();  // the staging buffer is rewritten by the next chunk
+                if (c == CHUNKS - 1) {
+                    // every TMEM read of this warp for this tile is done: hand the accumulator back to the leader's MMA warp
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(&tempty_bar[acc], 0);
+                }
+                // ---- bias (+ scale / GELU / positional) in registers; the column index is uniform across the warp
+                if (p.bias) {
+#pragma unroll
+                    for (int g = 0; g < CCOLS / 4; ++g) {
+                        if (n + 4 * g < p.N) {
+                            const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4 * g));
+                            v[4 * g + 0] += bv.x; v[4 * g + 1] += bv.y; v[4 * g + 2] += bv.z; v[4 * g + 3] += bv.w;
+                        }
+                    }
+                }
+                if constexpr (EPI == EPI_BIAS_F16) {
+#pragma unroll
+                    for (int j = 0; j < CCOLS; ++j) v[j] *= (n + j < p.scale_cols) ? p.scale : 1.0f;
+                }
+                if constexpr (EPI == EPI_BIAS_GELU_F16 || EPI == EPI_BIAS_GELU_POS_F32) {
+#pragma unroll
+                    for (int j = 0; j < CCOLS; ++j) v[j] = gelu_tanh(v[j]);
+                }
+                if constexpr (EPI == EPI_BIAS_GELU_POS_F32) {
+                    const int m = m0 + lane;
+                    if (m < p.M) {
+                        const float* pr = p.pos + static_cast<size_t>(m % p.pos_period) * p.N + n;
+#pragma unroll
+                        for (int g = 0; g < CCOLS / 4; ++g) {
+                            if (n + 4 * g < p.N) {
+                                const float4 pv = __ldg(reinterpret_cast<const float4*>(pr + 4 * g));
+                                v[4 * g + 0] += pv.x; v[4 * g + 1] += pv.y; v[4 * g + 2] += pv.z; v[4 * g + 3] += pv.w;
+                            }
+                        }
+                    }
+                }
+                // ---- the chunk buffer: wait for the residual rows (RESID) / for the store that last read this buffer
+                if constexpr (RESID) {
+                    mbar_wait(&my_rbar[b], static_cast<uint32_t>((gc / EPI_BUFS) & 1));
+#pragma unroll
+                    for (int g = 0; g < 8; ++g) {
+                        const float4 rv = *reinterpret_cast<const float4*>(buf + row_off + ((static_cast<uint32_t>(g) ^ sw) << 4));
+                        v[4 * g + 0] += rv.x; v[4 * g + 1] += rv.y; v[4 * g + 2] += rv.z; v[4 * g + 3] += rv.w;
+                    }
+                } else {
+                    // buffer b was last read by the store of chunk gc - EPI_BUFS; at most EPI_BUFS - 1 newer groups may still be pending
+                    if (lane == 0) bulk_wait_group_read<EPI_BUFS - 1>();
+                    __syncwarp();
+                }
+                // ---- write the 128-byte row of this chunk, 16-byte pieces XOR-swizzled like SWIZZLE_128B expects
+                if constexpr (F16OUT) {
+#pragma unroll
+                    for (int g = 0; g < 8; ++g) {
+                        uint4 pk;
+                        __half2 h0 = __floats2half2_rn(v[8 * g + 0], v[8 * g + 1]);
+                        __half2 h1 = __floats2half2_rn(v[8 * g + 2], v[8 * g + 3]);
+                        __half2 h2 = __floats2half2_rn(v[8 * g + 4], v[8 * g + 5]);
+                        __half2 h3 = __floats2half2_rn(v[8 * g + 6], v[8 * g + 7]);
+                        pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+                        pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+                        *reinterpret_cast<uint4*>(buf + row_off + ((static_cast<uint32_t>(g) ^ sw) << 4)) = pk;
+                    }
+                } else {
+#pragma unroll
+                    for (int g = 0; g < 8; ++g)
+                        *reinterpret_cast<float4*>(buf + row_off + ((static_cast<uint32_t>(g) ^ sw) << 4)) =
+                            make_float4(v[4 * g + 0], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    if (n < p.N) tma_store_2d(&tmO, buf, n, m0);   // rows >= M / columns >= N are clipped by the TMA unit
+                    bulk_commit_group();
+                    if constexpr (RESID) {
+                        // the buffer of chunk gc+2 was last read by the store of chunk gc-1: wait for it, then prefetch into it
+                        bulk_wait_group_read<1>();
+                        prefetch_resid(gc + 2);
+                    }
+                }
             }
-            // all TMEM reads of this warp are complete (wait::ld above): hand the accumulator back
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
         }
+        if (lane == 0) bulk_wait_group<0>();   // all stores complete before the CTA may exit
+        __syncwarp();
     }
 
     tc_fence_before();
-    __syncthreads();
+    cluster_sync_all();          // no CTA leaves (or frees TMEM) while its peer may still signal it
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, TMEM_COLS);
+        tmem_dealloc_cta2(tmem_base, TMEM_COLS);
     }
 }
 
@@ -281,17 +343,17 @@ PFN_encodeTiled get_encode_fn() {
     return fn;
 }
 
-// 2-D f16 row-major [rows, cols] with leading dimension ld (elements); box = box_rows x 64 columns, 128B swizzle
-bool make_tmap_f16_2d(CUtensorMap* tm, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+// 2-D row-major [rows, cols] with leading dimension ld (elements); box = box_rows x box_cols (128 bytes wide), 128B swizzle
+bool make_tmap_2d(CUtensorMap* tm, const void* ptr, CUtensorMapDataType dt, size_t esize, uint64_t rows, uint64_t cols, uint64_t ld,
+                  uint32_t box_rows, uint32_t box_cols) {
     PFN_encodeTiled enc = get_encode_fn();
     if (!enc) return false;
     cuuint64_t dims[2] = {cols, rows};
-    cuuint64_t strides[1] = {ld * sizeof(__half)};
-    cuuint32_t box[2] = {static_cast<cuuint32_t>(BK), box_rows};
+    cuuint64_t strides[1] = {ld * esize};
+    cuuint32_t box[2] = {box_cols, box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = enc(tm, dt, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS;
 }
 
@@ -299,7 +361,8 @@ std::atomic<int> g_launches{0};
 int g_num_sms = 0;
 
 template <int EPI>
-cudaError_t launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const KParams& kp, cudaStream_t st) {
+cudaError_t launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const CUtensorMap& tmR, const KParams& kp,
+                   cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(gemm_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
@@ -312,8 +375,9 @@ cudaError_t launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const KParams
         cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
     }
     const int tiles = kp.m_tiles * kp.n_tiles;
-    const int grid = tiles < g_num_sms ? tiles : g_num_sms;
-    gemm_kernel<EPI><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmA, tmB, kp);
+    const int max_clusters = g_num_sms / 2;
+    const int clusters = tiles < max_clusters ? tiles : max_clusters;
+    gemm_kernel<EPI><<<2 * clusters, NUM_THREADS, SMEM_BYTES, st>>>(tmA, tmB, tmO, tmR, kp);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return cudaGetLastError();
 }
@@ -327,26 +391,36 @@ cudaError_t gemm_f16_tcgen05(const GemmArgs& a, GemmEpilogue epi, cudaStream_t s
     if ((a.K % 8) || (a.N % 8) || (a.lda % 8) || (a.ldw % 8) || (a.ldo % 8)) return cudaErrorInvalidValue;
     if ((reinterpret_cast<uintptr_t>(a.A) | reinterpret_cast<uintptr_t>(a.W) | reinterpret_cast<uintptr_t>(a.out)) & 15)
         return cudaErrorMisalignedAddress;
-    CUtensorMap tmA, tmB;
-    if (!make_tmap_f16_2d(&tmA, a.A, a.M, a.K, a.lda, BM)) return cudaErrorInvalidValue;
-    if (!make_tmap_f16_2d(&tmB, a.W, a.N, a.K, a.ldw, BN)) return cudaErrorInvalidValue;
+    const bool f16out = (epi == EPI_BIAS_F16 || epi == EPI_BIAS_GELU_F16);
+    CUtensorMap tmA, tmB, tmO, tmR;
+    if (!make_tmap_2d(&tmA, a.A, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, a.M, a.K, a.lda, BM, BK)) return cudaErrorInvalidValue;
+    if (!make_tmap_2d(&tmB, a.W, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, a.N, a.K, a.ldw, BN / 2, BK)) return cudaErrorInvalidValue;
+    if (f16out) {
+        if (!make_tmap_2d(&tmO, a.out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, a.M, a.N, a.ldo, 32, 64)) return cudaErrorInvalidValue;
+    } else {
+        if (!make_tmap_2d(&tmO, a.out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a.M, a.N, a.ldo, 32, 32)) return cudaErrorInvalidValue;
+    }
+    tmR = tmO;
+    if (epi == EPI_BIAS_RESID_F32) {
+        if (!a.resid) return cudaErrorInvalidValue;
+        if (reinterpret_cast<uintptr_t>(a.resid) & 15) return cudaErrorMisalignedAddress;
+        if (!make_tmap_2d(&tmR, a.resid, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a.M, a.N, a.ldo, 32, 32)) return cudaErrorInvalidValue;
+    }
     KParams kp;
     kp.M = a.M; kp.N = a.N; kp.K = a.K;
-    kp.bias = a.bias; kp.out = a.out; kp.ldo = a.ldo; kp.resid = a.resid;
+    kp.bias = a.bias;
     kp.pos = a.pos; kp.pos_period = a.pos_period > 0 ? a.pos_period : 1;
     kp.scale_cols = a.scale_cols; kp.scale = a.scale;
-    kp.m_tiles = (a.M + BM - 1) / BM;
+    kp.m_tiles = (a.M + 2 * BM - 1) / (2 * BM);
     kp.n_tiles = (a.N + BN - 1) / BN;
     switch (epi) {
-        case EPI_BIAS_F16:          return launch<EPI_BIAS_F16>(tmA, tmB, kp, st);
-        case EPI_BIAS_GELU_F16:     return launch<EPI_BIAS_GELU_F16>(tmA, tmB, kp, st);
-        case EPI_BIAS_RESID_F32:
-            if (!a.resid) return cudaErrorInvalidValue;
-            return launch<EPI_BIAS_RESID_F32>(tmA, tmB, kp, st);
+        case EPI_BIAS_F16:          return launch<EPI_BIAS_F16>(tmA, tmB, tmO, tmR, kp, st);
+        case EPI_BIAS_GELU_F16:     return launch<EPI_BIAS_GELU_F16>(tmA, tmB, tmO, tmR, kp, st);
+        case EPI_BIAS_RESID_F32:    return launch<EPI_BIAS_RESID_F32>(tmA, tmB, tmO, tmR, kp, st);
         case EPI_BIAS_GELU_POS_F32:
             if (!a.pos) return cudaErrorInvalidValue;
-            return launch<EPI_BIAS_GELU_POS_F32>(tmA, tmB, kp, st);
-        case EPI_BIAS_F32:          return launch<EPI_BIAS_F32>(tmA, tmB, kp, st);
+            return launch<EPI_BIAS_GELU_POS_F32>(tmA, tmB, tmO, tmR, kp, st);
+        case EPI_BIAS_F32:          return launch<EPI_BIAS_F32>(tmA, tmB, tmO, tmR, kp, st);
     }
     return cudaErrorInvalidValue;
 }
