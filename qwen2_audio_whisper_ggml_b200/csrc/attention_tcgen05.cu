@@ -220,14 +220,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm, __half* __restrict__
             }
             const bool any_need = __any_sync(0xffffffffu, need);
             // ---- probabilities
-            float rs4[4] = {0.f, 0.f, 0.f, 0.f};
             uint32_t pk[4][16];
+            float rs4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int c4 = 0; c4 < 4; ++c4)
 #pragma unroll
                 for (int i = 0; i < 32; i += 2) {
-                    const float p0 = ex2(fmaf(__uint_as_float(s[c4][i]), LOG2E, -m_used));
-                    const float p1 = ex2(fmaf(__uint_as_float(s[c4][i + 1]), LOG2E, -m_used));
+                    const float x0 = fmaf(__uint_as_float(s[c4][i]), LOG2E, -m_used);
+                    const float x1 = fmaf(__uint_as_float(s[c4][i + 1]), LOG2E, -m_used);
+                    const float p0 = ex2(x0);
+                    const float p1 = ex2(x1);
                     rs4[c4] += p0 + p1;
                     __half2 hh = __floats2half2_rn(p0, p1);
                     pk[c4][i >> 1] = *reinterpret_cast<uint32_t*>(&hh);
