@@ -195,7 +195,9 @@ WHISPER_API int whisper_embd_dims(struct whisper_context * ctx, int * n_windows,
 WHISPER_API int whisper_get_embeddings(struct whisper_context * ctx, float * dst, size_t n_floats);            /* copies to host */
 WHISPER_API int whisper_get_embeddings_from_state(struct whisper_state * state, float * dst, size_t n_floats);
 WHISPER_API const float * whisper_get_embeddings_device(struct whisper_context * ctx);                       /* device pointer */
-/* mel of the default state, float[n_mel][n_len] */
+/* mel of the default state, float[n_mel][n_len]; n_len is the padded length (n_samples + 30 s) / 160, whereas whisper_n_len()
+ * returns n_len_org like the reference (src:3440-3446) */
+WHISPER_API int whisper_get_mel_dims(struct whisper_context * ctx, int * n_len, int * n_len_org, int * n_mel);
 WHISPER_API int whisper_get_mel(struct whisper_context * ctx, float * dst, size_t n_floats);
 /* B independent 30 s windows of PCM (window b at samples + b*stride, n_samples[b] valid, NULL = full windows):
  * per-window mel + encoder, results [B][n_out][n_state] copied to dst if non-NULL.  max windows per micro-batch is

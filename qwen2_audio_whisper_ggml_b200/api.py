@@ -72,6 +72,7 @@ _WSIGS = {
     "whisper_get_embeddings_from_state": (_i, [_vp, _vp, _sz]),
     "whisper_get_embeddings_device": (_vp, [_vp]),
     "whisper_get_mel": (_i, [_vp, _vp, _sz]),
+    "whisper_get_mel_dims": (_i, [_vp, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
     "whisper_encode_batch": (_i, [_vp, _vp, _sz, _vp, _i, _vp]),
     "whisper_encode_batch_device": (_i, [_vp, _vp, _sz, _vp, _i]),
     "whisper_set_max_batch": (_i, [_vp, _i]),
@@ -200,8 +201,15 @@ class Context:
             raise _l.Q2WError(-1, "whisper_get_embeddings failed (see log)")
         return out
 
+    def mel_dims(self):
+        """(n_len, n_len_org, n_mel) of the default state's mel"""
+        a, b, c = _i(), _i(), _i()
+        if wlib().whisper_get_mel_dims(self._h, C.byref(a), C.byref(b), C.byref(c)) != 0:
+            raise _l.Q2WError(-1, "whisper_get_mel_dims failed")
+        return a.value, b.value, c.value
+
     def get_mel(self) -> np.ndarray:
-        n_len, n_mel = self.n_len(), self.model_n("n_mels")
+        n_len, _, n_mel = self.mel_dims()
         out = np.empty((n_mel, n_len), dtype=np.float32)
         if wlib().whisper_get_mel(self._h, out.ctypes.data, out.size) != 0:
             raise _l.Q2WError(-1, "whisper_get_mel failed (see log)")
@@ -222,6 +230,18 @@ class Context:
         if rc != 0:
             raise _l.Q2WError(rc, "whisper_encode_batch failed (see log)")
         return out
+
+    def encode_long(self, samples, out: np.ndarray | None = None) -> np.ndarray:
+        """Audio of any length: cut into 30 s windows (the last one ragged), each with its own mel normalisation, and run
+        them as one batch (BASELINE config 5; the fork itself never iterates past the first window)."""
+        s = _f32(samples).reshape(-1)
+        win = 2 * self.model_n("n_audio_ctx") * 160
+        nw = max(1, -(-s.size // win))
+        padded = np.zeros((nw, win), dtype=np.float32)
+        padded.reshape(-1)[: s.size] = s
+        ns = np.full(nw, win, dtype=np.int32)
+        ns[-1] = s.size - (nw - 1) * win
+        return self.encode_batch(padded, ns, out=out)
 
     def encode_batch_device(self, dev_ptr: int, stride: int, B: int, n_samples=None) -> int:
         ns = None if n_samples is None else np.ascontiguousarray(n_samples, dtype=np.int32)

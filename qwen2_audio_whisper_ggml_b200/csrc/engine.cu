@@ -12,6 +12,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -110,8 +111,10 @@ struct q2w_state {
     __half* att = nullptr;     // [B*T, D]         (aliases conv1 operand A1)
     __half* h = nullptr;       // [B*T, 4D]        (aliases conv1 output h1 [B*T2, D])
     __half* wscratch = nullptr;  // decoded weight matrix (largest: 4D*D)
-    float* pcm_dev = nullptr;  // [B, win_samples]
-    int* nsamp_dev = nullptr;  // [B]
+    float* pcm_dev = nullptr;  // [2][B, win_samples]  double-buffered host staging (copy of micro-batch i+1 overlaps compute of i)
+    int* nsamp_dev = nullptr;  // [2][B]
+    cudaStream_t s_in = nullptr, s_out = nullptr;   // copy-in / copy-out streams of the host-buffer batch path
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
     float* logmel = nullptr;   // [B, n_mel, ld_mel]
     float* winmax = nullptr;   // [B] ordered int keys
     // results
@@ -277,11 +280,11 @@ int ensure_emb(q2w_state* s, int n_windows) {
 }
 
 // mel + conv1 operand for Bm windows resident in s->pcm_dev, then the encoder
-int batch_chunk(q2w_state* s, const float* pcm_dev, size_t stride, int Bm, int w0) {
+int batch_chunk(q2w_state* s, const float* pcm_dev, size_t stride, const int* nsamp_dev, int Bm, int w0) {
     {
         // algorithmic bytes: PCM in + used mel frames out (4*480000 + 4*128*3000 per window)
         ProfScope ps(s, PC_MEL, 0.0, static_cast<double>(Bm) * (4.0 * s->win_samples + 4.0 * s->n_mel * s->T2));
-        CKL(mel_logpower(s->m->mel, pcm_dev, stride, s->nsamp_dev, s->win_samples, Bm, s->n_frames_batch, s->logmel, s->ld_mel,
+        CKL(mel_logpower(s->m->mel, pcm_dev, stride, nsamp_dev, s->win_samples, Bm, s->n_frames_batch, s->logmel, s->ld_mel,
                          s->winmax, s->stream));
         g_launches.fetch_add(1);  // mel_logpower issues two kernels (key init + main)
     }
@@ -490,8 +493,14 @@ int q2w_state_create(q2w_state** out, q2w_model* m, int max_batch) {
     SALLOC(s->att, B * att_elems * sizeof(__half));
     SALLOC(s->h, B * T * 4 * D * sizeof(__half));
     SALLOC(s->wscratch, wmax * sizeof(__half));
-    SALLOC(s->pcm_dev, B * s->win_samples * sizeof(float));
-    SALLOC(s->nsamp_dev, B * sizeof(int));
+    SALLOC(s->pcm_dev, 2 * B * s->win_samples * sizeof(float));
+    SALLOC(s->nsamp_dev, 2 * B * sizeof(int));
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->s_in, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->s_out, cudaStreamNonBlocking);
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+        e = cudaEventCreateWithFlags(&s->ev_in[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_done[i], cudaEventDisableTiming);
+    }
     SALLOC(s->logmel, B * s->n_mel * s->ld_mel * sizeof(float));
     SALLOC(s->winmax, B * sizeof(float));
     SALLOC(s->api_max, sizeof(float));
@@ -512,6 +521,9 @@ void q2w_state_free(q2w_state* s) {
                     s->emb, s->api_mel, s->api_pcm, s->api_max};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& r : s->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    for (int i = 0; i < 2; ++i) { if (s->ev_in[i]) cudaEventDestroy(s->ev_in[i]); if (s->ev_done[i]) cudaEventDestroy(s->ev_done[i]); }
+    if (s->s_in) cudaStreamDestroy(s->s_in);
+    if (s->s_out) cudaStreamDestroy(s->s_out);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
 }
@@ -612,25 +624,45 @@ static int encode_batch_impl(q2w_state* s, const float* pcm, bool pcm_on_host, s
         ns[b] = n;
     }
     const size_t out_per_window = static_cast<size_t>(s->T / 2) * s->D;
-    for (int w0 = 0; w0 < B; w0 += s->max_batch) {
-        const int Bm = std::min(s->max_batch, B - w0);
-        CK(cudaMemcpyAsync(s->nsamp_dev, ns.data() + w0, sizeof(int) * Bm, cudaMemcpyHostToDevice, s->stream));
+    // micro-batches: at most max_batch windows each.  With host buffers a batch that would fit in one micro-batch is still cut
+    // in two, so the H2D copy of the second half and the D2H copy of the first half's embeddings overlap compute.
+    int mb = std::min(s->max_batch, B);
+    if (pcm_on_host && B <= s->max_batch && B >= 16) {
+        static int split = -1;
+        if (split < 0) { const char* e = getenv("Q2W_E2E_SPLIT"); split = e ? std::max(1, atoi(e)) : 2; }
+        mb = (B + split - 1) / split;
+    }
+    int it = 0;
+    for (int w0 = 0; w0 < B; w0 += mb, ++it) {
+        const int Bm = std::min(mb, B - w0);
+        const int slot = it & 1;
+        int* nsamp = s->nsamp_dev + static_cast<size_t>(slot) * s->max_batch;
         const float* pcm_dev = nullptr;
         size_t dev_stride = stride;
         if (pcm_on_host) {
-            CK(cudaMemcpy2DAsync(s->pcm_dev, static_cast<size_t>(s->win_samples) * sizeof(float), pcm + static_cast<size_t>(w0) * stride,
-                                 stride * sizeof(float), width * sizeof(float), Bm, cudaMemcpyHostToDevice, s->stream));
-            pcm_dev = s->pcm_dev;
+            float* stage = s->pcm_dev + static_cast<size_t>(slot) * s->max_batch * s->win_samples;
+            if (it >= 2) CK(cudaStreamWaitEvent(s->s_in, s->ev_done[slot], 0));   // compute of micro-batch it-2 has consumed this slot
+            CK(cudaMemcpyAsync(nsamp, ns.data() + w0, sizeof(int) * Bm, cudaMemcpyHostToDevice, s->s_in));
+            CK(cudaMemcpy2DAsync(stage, static_cast<size_t>(s->win_samples) * sizeof(float), pcm + static_cast<size_t>(w0) * stride,
+                                 stride * sizeof(float), width * sizeof(float), Bm, cudaMemcpyHostToDevice, s->s_in));
+            CK(cudaEventRecord(s->ev_in[slot], s->s_in));
+            CK(cudaStreamWaitEvent(s->stream, s->ev_in[slot], 0));
+            pcm_dev = stage;
             dev_stride = s->win_samples;
         } else {
+            if (it >= 2) CK(cudaStreamWaitEvent(s->stream, s->ev_done[slot], 0));
+            CK(cudaMemcpyAsync(nsamp, ns.data() + w0, sizeof(int) * Bm, cudaMemcpyHostToDevice, s->stream));
             pcm_dev = pcm + static_cast<size_t>(w0) * stride;
         }
-        if ((rc = batch_chunk(s, pcm_dev, dev_stride, Bm, w0))) return rc;
+        if ((rc = batch_chunk(s, pcm_dev, dev_stride, nsamp, Bm, w0))) return rc;
+        CK(cudaEventRecord(s->ev_done[slot], s->stream));
         if (out_host) {
+            CK(cudaStreamWaitEvent(s->s_out, s->ev_done[slot], 0));
             CK(cudaMemcpyAsync(out_host + static_cast<size_t>(w0) * out_per_window, s->emb + static_cast<size_t>(w0) * out_per_window,
-                               static_cast<size_t>(Bm) * out_per_window * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+                               static_cast<size_t>(Bm) * out_per_window * sizeof(float), cudaMemcpyDeviceToHost, s->s_out));
         }
     }
+    if (out_host) CK(cudaStreamSynchronize(s->s_out));
     CK(cudaStreamSynchronize(s->stream));
     s->emb_windows = B;
     s->t_encode_us += now_us() - t0;

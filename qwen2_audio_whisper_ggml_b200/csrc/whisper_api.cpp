@@ -467,7 +467,9 @@ int whisper_full(struct whisper_context* ctx, struct whisper_full_params params,
 }
 
 // ------------------------------------------------------------------------------------------------ getters
-int whisper_n_len_from_state(struct whisper_state* state) { return state ? q2w_mel_n_len(state->qs) : 0; }
+// the reference returns mel.n_len_org here (src/qwen2-whisper.cpp:3440-3446): frames that carry audio, not the 30 s-padded length,
+// which is what makes whisper_full skip clips shorter than ~1 s (:2357-2365)
+int whisper_n_len_from_state(struct whisper_state* state) { return state ? q2w_mel_n_len_org(state->qs) : 0; }
 int whisper_n_len(struct whisper_context* ctx) { return ctx ? whisper_n_len_from_state(ctx->state) : 0; }
 int whisper_n_vocab(struct whisper_context* ctx) { return ctx->hp.n_vocab; }
 int whisper_n_text_ctx(struct whisper_context* ctx) { return ctx->hp.n_text_ctx; }
@@ -555,6 +557,13 @@ int whisper_get_mel(struct whisper_context* ctx, float* dst, size_t n_floats) {
         LOG_ERROR("%s: %s\n", __func__, q2w_last_error());
         return -1;
     }
+    return 0;
+}
+int whisper_get_mel_dims(struct whisper_context* ctx, int* n_len, int* n_len_org, int* n_mel) {
+    if (!ctx || !ctx->state) return -1;
+    if (n_len) *n_len = q2w_mel_n_len(ctx->state->qs);
+    if (n_len_org) *n_len_org = q2w_mel_n_len_org(ctx->state->qs);
+    if (n_mel) *n_mel = ctx->hp.n_mels;
     return 0;
 }
 int whisper_set_max_batch(struct whisper_context* ctx, int max_batch) {

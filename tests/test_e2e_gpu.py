@@ -38,7 +38,8 @@ def test_tiny_full_vs_golden(wname):
     ctx, _ = tiny_ctx(wname)
     pcm = synth.synth_pcm(32000, seed=3)
     assert ctx.full(pcm) == 0
-    assert ctx.n_len() == int(g["n_len"])
+    assert ctx.mel_dims()[0] == int(g["n_len"])
+    assert ctx.n_len() == 1 + (32000 + 200 - 400) // 160          # whisper_n_len == n_len_org (src:3440-3446)
     mel = ctx.get_mel()
     assert max_abs(mel[:, :220], g["mel"]) < TOL["mel"]["max_abs"]
     emb = ctx.get_embeddings()
@@ -89,14 +90,20 @@ def test_tiny_live_reference_offsets_and_set_mel(ref):
     rctx.free()
 
 
-def test_short_audio_returns_zero_and_does_nothing():
-    ctx, _ = tiny_ctx("f16")
+def test_short_audio_returns_zero_and_does_nothing(ref):
+    ctx, buf = tiny_ctx("f16")
     p = api.wlib().whisper_full_default_params()
     p.offset_ms = 0
     p.duration_ms = 500           # < 1000 ms -> warning + 0 (:2362-2365)
-    assert ctx.full(synth.synth_pcm(16000, seed=1), params=p) == 0
-    nw, _, _ = ctx.embd_dims()
-    assert nw == 0
+    assert ctx.full(synth.synth_pcm(32000, seed=1), params=p) == 0
+    assert ctx.embd_dims()[0] == 0
+    # a 12345-sample clip has n_len_org = 76 < 100 frames: the reference returns 0 without running the encoder, and so do we
+    short = synth.synth_pcm(12345, seed=2, kind="noise")
+    rctx = ref.RefContext(buf)
+    assert rctx.full(short) == 0 and rctx.timings()["n_encode"] == 0      # returned 0 but never ran the encoder
+    assert ctx.full(short) == 0 and ctx.embd_dims()[0] == 0
+    assert ctx.n_len() == rctx.mel_dims()[1] == 76
+    rctx.free()
     ctx.free()
 
 
@@ -115,9 +122,10 @@ def test_batch_equals_single_windows_bitwise():
     out8 = ctx.encode_batch(pcm, ns)
     assert np.array_equal(out, out8)
     for b in range(B):
-        assert ctx.full(pcm[b, :ns[b]]) == 0
+        # whisper_pcm_to_mel + whisper_encode (whisper_full would skip the clips under 1 s: n_len_org < 100, src:2362)
+        assert ctx.pcm_to_mel(pcm[b, :ns[b]]) == 0 and ctx.encode(0) == 0
         single = ctx.get_embeddings()[0]
-        # whisper_full computes the mel over n + 30 s of padding, the batch API over one window: same frames, same max
+        # the API mel covers n + 30 s of padding, the batch API one window: same frames, same max
         assert rel_l2(out[b], single) < 1e-6, (b, rel_l2(out[b], single))
     ctx.free()
 
@@ -178,3 +186,69 @@ def test_full_size_vs_golden(wname):
     assert rel_l2(out[0], emb) < 1e-6 and np.array_equal(out[0], out[1]) and np.array_equal(out[0], out[3])
     assert np.isfinite(out[2]).all()
     ctx.free()
+
+
+def test_long_audio_chunked_equals_per_window_reference(ref):
+    """BASELINE config 5 semantics: long PCM cut into windows, per-window mel max; each window == the reference on that window"""
+    ctx, buf = tiny_ctx("f16", seed=3)
+    rctx = ref.RefContext(buf)
+    win = 200 * 160
+    pcm = synth.synth_pcm(3 * win + 20000, seed=77, kind="noise")   # ragged tail >= 1 s (the reference skips shorter clips)
+    out = ctx.encode_long(pcm)
+    assert out.shape == (4, 50, 128)
+    for w in range(4):
+        seg = pcm[w * win:(w + 1) * win]
+        assert rctx.full(seg) == 0
+        assert rel_l2(out[w], rctx.get_embeddings()) < TOL["f16"]["rel_l2"], w
+    ctx.free()
+    rctx.free()
+
+
+def test_second_state_shares_the_model():
+    """several states over one read-only model (src/qwen2-whisper.cpp:769-770), whisper_init_state / whisper_free_state"""
+    import ctypes as C
+    ctx, _ = tiny_ctx("f16")
+    w = api.wlib()
+    st = w.whisper_init_state(ctx._h)
+    assert st
+    a = synth.synth_pcm(32000, seed=5)
+    b = synth.synth_pcm(32000, seed=6, kind="noise")
+    p = w.whisper_full_default_params()
+    assert ctx.full(a) == 0
+    assert w.whisper_full_with_state(ctx._h, st, p, b.ctypes.data, b.size) == 0
+    e_default = ctx.get_embeddings()[0]
+    e_state = np.empty_like(e_default)
+    assert w.whisper_get_embeddings_from_state(st, e_state.ctypes.data, e_state.size) == 0
+    assert ctx.full(b) == 0
+    assert np.array_equal(ctx.get_embeddings()[0], e_state) and not np.array_equal(e_default, e_state)
+    assert w.whisper_n_len_from_state(st) == ctx.n_len()
+    w.whisper_free_state(st)
+    ctx.free()
+
+
+def test_cli_matches_reference_printout(ref, tmp_path, capfd):
+    """q2w-main (examples/main equivalent): WAV in, ' %.3f' x 20 out -- the reference's only user-visible check"""
+    import subprocess
+    import wave
+    exe = os.path.join(os.path.dirname(GOLD), "..", "qwen2_audio_whisper_ggml_b200", "q2w-main")
+    exe = os.path.abspath(exe)
+    if not os.path.exists(exe):
+        pytest.skip("q2w-main not built")
+    mf = synth.synth_model(synth.TINY_HPARAMS, gq.GGML_TYPE_F16, seed=1)
+    model = tmp_path / "tiny-f16.bin"
+    mfm.save(str(model), mf)
+    pcm = synth.synth_pcm(40000, seed=9)
+    wav = tmp_path / "a.wav"
+    with wave.open(str(wav), "wb") as wf:
+        wf.setnchannels(1); wf.setsampwidth(2); wf.setframerate(16000)
+        wf.writeframes(np.round(pcm * 32768.0).astype(np.int16).tobytes())
+    r = subprocess.run([exe, "-m", str(model), "-f", str(wav), "-n", "2", "-np"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 2 and lines[0] == lines[1]
+    got = np.array([float(x) for x in lines[0].split()])
+    rctx = ref.RefContext(mfm.to_bytes(mf))
+    assert rctx.full(pcm) == 0
+    want = rctx.get_embeddings().reshape(-1)[:20]
+    assert got.shape == (20,) and np.abs(got - want).max() < 5e-3      # %.3f rounding + F16 tolerance
+    rctx.free()
