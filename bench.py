@@ -249,6 +249,24 @@ def main():
         if i >= 3:
             lat.append(a0.elapsed_time(a1))
 
+    # ---- optional: gather every rank's embeddings on rank 0 over NCCL (the only collective this path ever issues; NOT part of
+    #      the timed region -- SURVEY 8(e): "NCCL only to gather embeddings when a caller asks for them on one device")
+    gather_ms = None
+    if world > 1:
+        emb = torch.empty((B, 750, 1280), dtype=torch.float32, device="cuda")
+        step_device()
+        torch.cuda.cudart().cudaMemcpy(emb.data_ptr(), ctx.embeddings_device_ptr(), emb.numel() * 4, 3)   # cudaMemcpyDeviceToDevice
+        parts = [torch.empty_like(emb) for _ in range(world)] if rank == 0 else None
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        dist.gather(emb, parts, dst=0)
+        g1.record()
+        torch.cuda.synchronize()
+        gather_ms = g0.elapsed_time(g1)
+        if rank == 0:
+            assert all(torch.isfinite(p_).all() for p_ in parts) and torch.equal(parts[0], emb)
+
     t = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -296,7 +314,7 @@ def main():
                         "ms_per_step": 1e3 * e2e_s / a.steps},
                 "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline, "kernels": kernels,
                 "p50_ms_per_window_b1": statistics.median(lat), "ms_per_window": dev_ms / a.steps / B,
-                "tflops_whole_step": 2.2738 * B * a.steps / (dev_ms / 1e3) / 1e0 * 1.0, "setup_s": setup_s}
+                "nccl_gather_ms": gather_ms, "setup_s": setup_s}
         line["tflops_whole_step"] = 2.2738e12 * B * a.steps / (dev_ms / 1e3) / 1e12
         print(json.dumps(line))
     ctx.free()

@@ -128,6 +128,10 @@ struct q2w_state {
     float* api_pcm = nullptr;
     size_t api_pcm_cap = 0;
     float* api_max = nullptr;
+    // CUDA graph of the single-window forward (launch-bound: ~330 kernels of 5-25 us each); captured on the second B = 1 call
+    cudaGraphExec_t g1 = nullptr;
+    float* g1_emb = nullptr;
+    int g1_state = 0;          // 0 cold, 1 warmed eagerly, 2 graph ready, -1 capture failed (stay eager)
     // timers
     int64_t t_mel_us = 0, t_encode_us = 0;
     int32_t n_encode = 0;
@@ -204,8 +208,40 @@ int weight_gemm(q2w_state* s, const __half* A, int lda, const void* W, int wtype
     return Q2W_OK;
 }
 
+int forward_eager(q2w_state* s, int Bm, int w0);
+
 // conv stem + encoder for Bm windows whose conv1 operand A1 (in s->att) is ready; writes emb rows [w0, w0+Bm)
 int forward_from_a1(q2w_state* s, int Bm, int w0) {
+    if (Bm != 1 || w0 != 0 || s->prof_on || s->g1_state < 0) return forward_eager(s, Bm, w0);
+    if (s->g1_state == 2 && s->g1_emb == s->emb) {
+        CK(cudaGraphLaunch(s->g1, s->stream));
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        return Q2W_OK;
+    }
+    if (s->g1_state == 0) {            // first call runs eagerly: one-time function attributes / driver entry points get resolved
+        s->g1_state = 1;
+        return forward_eager(s, Bm, w0);
+    }
+    if (s->g1) { cudaGraphExecDestroy(s->g1); s->g1 = nullptr; }
+    cudaGraph_t graph = nullptr;
+    if (cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); s->g1_state = -1; return forward_eager(s, Bm, w0); }
+    const int rc = forward_eager(s, Bm, w0);
+    const cudaError_t e = cudaStreamEndCapture(s->stream, &graph);
+    if (rc != Q2W_OK || e != cudaSuccess || !graph || cudaGraphInstantiate(&s->g1, graph, 0) != cudaSuccess) {
+        cudaGetLastError();
+        if (graph) cudaGraphDestroy(graph);
+        s->g1 = nullptr;
+        s->g1_state = -1;
+        return forward_eager(s, Bm, w0);
+    }
+    cudaGraphDestroy(graph);
+    s->g1_state = 2;
+    s->g1_emb = s->emb;
+    CK(cudaGraphLaunch(s->g1, s->stream));
+    return Q2W_OK;
+}
+
+int forward_eager(q2w_state* s, int Bm, int w0) {
     q2w_model* m = s->m;
     const int T = s->T, T2 = s->T2, D = s->D, H = s->H, FF = s->FF;
     const int M = Bm * T;
@@ -521,6 +557,7 @@ void q2w_state_free(q2w_state* s) {
                     s->emb, s->api_mel, s->api_pcm, s->api_max};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& r : s->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    if (s->g1) cudaGraphExecDestroy(s->g1);
     for (int i = 0; i < 2; ++i) { if (s->ev_in[i]) cudaEventDestroy(s->ev_in[i]); if (s->ev_done[i]) cudaEventDestroy(s->ev_done[i]); }
     if (s->s_in) cudaStreamDestroy(s->s_in);
     if (s->s_out) cudaStreamDestroy(s->s_out);
