@@ -123,6 +123,9 @@ Q2W_API const char* q2w_build_info(void);
 Q2W_API int q2w_op_gemm(const void* A_f16, int lda, const void* W_f16, int ldw, int M, int N, int K, const float* bias,
                         void* out, int ldo, int epilogue, const float* resid, const float* pos, int pos_period,
                         int scale_cols, float scale, void* stream);
+/* same GEMM with W as raw ggml blocks (wtype = Q2W_TYPE_Q8_0 / Q2W_TYPE_Q4_0, K % 64 == 0): decoded inside the kernel */
+Q2W_API int q2w_op_gemm_q(const void* A_f16, int lda, const void* W_raw, int wtype, int M, int N, int K, const float* bias,
+                          void* out, int ldo, int epilogue, const float* resid, int scale_cols, float scale, void* stream);
 Q2W_API int q2w_op_layernorm(const float* x, const float* gamma, const float* beta, void* y_f16, int M, int D, float eps,
                              void* stream);
 Q2W_API int q2w_op_pool_layernorm(const float* x, const float* gamma, const float* beta, float* y, int B, int T, int D,

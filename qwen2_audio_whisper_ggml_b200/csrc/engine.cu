@@ -195,14 +195,26 @@ int weight_gemm(q2w_state* s, const __half* A, int lda, const void* W, int wtype
                 void* out, int ldo, GemmEpilogue epi, const float* resid, const float* pos, int pos_period, int scale_cols,
                 float scale) {
     const __half* Wh = static_cast<const __half*>(W);
+    int gemm_wtype = Q2W_TYPE_F16;
     if (wtype_dev != Q2W_TYPE_F16) {
-        ProfScope ps(s, PC_DEQUANT, 0.0, static_cast<double>(type_row_bytes(wtype_dev, K)) * N + 2.0 * N * K);
-        CKL(dequant_to_f16(W, wtype_dev, s->wscratch, static_cast<size_t>(N), K, s->stream));
-        Wh = s->wscratch;
+        // Two decode strategies, both keep W quantised in HBM (measured at B = 64 on B200):
+        //   fused   raw ggml blocks go straight into the GEMM and are decoded by its dequant warpgroup (Q2W_FUSED_DEQUANT=1):
+        //           Q8_0 GEMMs 440 TFLOP/s -- every W tile is re-decoded by each of the 750 M-tiles that use it
+        //   scratch one decode pass per GEMM into a 13 MB L2-resident F16 scratch, then the TMA-fed F16 GEMM (default):
+        //           1205 TFLOP/s, the decode pass costs 1 % of the step
+        static int fused = -1;
+        if (fused < 0) { const char* e = getenv("Q2W_FUSED_DEQUANT"); fused = (e && atoi(e) != 0) ? 1 : 0; }
+        if (fused && K % 64 == 0) {
+            gemm_wtype = wtype_dev;
+        } else {
+            ProfScope ps(s, PC_DEQUANT, 0.0, static_cast<double>(type_row_bytes(wtype_dev, K)) * N + 2.0 * N * K);
+            CKL(dequant_to_f16(W, wtype_dev, s->wscratch, static_cast<size_t>(N), K, s->stream));
+            Wh = s->wscratch;
+        }
     }
     ProfScope ps(s, PC_GEMM, 2.0 * M * static_cast<double>(N) * K, 0.0);
     GemmArgs g{};
-    g.A = A; g.lda = lda; g.W = Wh; g.ldw = K; g.M = M; g.N = N; g.K = K; g.bias = bias; g.out = out; g.ldo = ldo;
+    g.A = A; g.lda = lda; g.W = Wh; g.ldw = K; g.wtype = gemm_wtype; g.M = M; g.N = N; g.K = K; g.bias = bias; g.out = out; g.ldo = ldo;
     g.resid = resid; g.pos = pos; g.pos_period = pos_period; g.scale_cols = scale_cols; g.scale = scale;
     CKL(gemm_f16_tcgen05(g, epi, s->stream));
     return Q2W_OK;
@@ -829,6 +841,15 @@ int q2w_op_gemm(const void* A, int lda, const void* W, int ldw, int M, int N, in
     g.A = static_cast<const __half*>(A); g.lda = lda; g.W = static_cast<const __half*>(W); g.ldw = ldw;
     g.M = M; g.N = N; g.K = K; g.bias = bias; g.out = out; g.ldo = ldo; g.resid = resid; g.pos = pos; g.pos_period = pos_period;
     g.scale_cols = scale_cols; g.scale = scale;
+    CKL(gemm_f16_tcgen05(g, static_cast<GemmEpilogue>(epilogue), static_cast<cudaStream_t>(stream)));
+    return Q2W_OK;
+}
+
+int q2w_op_gemm_q(const void* A, int lda, const void* W_raw, int wtype, int M, int N, int K, const float* bias, void* out, int ldo,
+                  int epilogue, const float* resid, int scale_cols, float scale, void* stream) {
+    GemmArgs g{};
+    g.A = static_cast<const __half*>(A); g.lda = lda; g.W = static_cast<const __half*>(W_raw); g.ldw = K; g.wtype = wtype;
+    g.M = M; g.N = N; g.K = K; g.bias = bias; g.out = out; g.ldo = ldo; g.resid = resid; g.scale_cols = scale_cols; g.scale = scale;
     CKL(gemm_f16_tcgen05(g, static_cast<GemmEpilogue>(epilogue), static_cast<cudaStream_t>(stream)));
     return Q2W_OK;
 }

@@ -13,6 +13,11 @@
 //   warp 1    MMA issuer (leader CTA only): tcgen05.mma.cta_group::2.kind::f16, M256 N256 K16; accumulators live in TMEM
 //             (128 lanes x 256 columns per CTA), double-buffered; tcgen05.commit ... multicast::cluster releases the smem
 //             stage / publishes the accumulator in both CTAs.
+//   warps 10-13 (quantised weights only) in-kernel ggml block decode: W stays Q8_0 / Q4_0 in HBM exactly as in the model file; each
+//             thread owns one row of this CTA's 128-row W half, reads its two 32-element blocks of the k-step (34 B / 18 B each,
+//             one k-step ahead), decodes them with the integer->F16 magic-number trick (q*d rounded once to F16, bit-identical
+//             to dequantize_row_q8_0 / q4_0 followed by an F16 store) and writes the 128-byte row into the SWIZZLE_128B tile
+//             the MMA reads; the smem stage becomes "full" when the A bytes of both CTAs AND the 8 decode warps have arrived.
 //   warps 2-9 epilogue, two per TMEM lane quadrant.  Everything stays in the "lane = output row" domain the accumulator
 //             arrives in: tcgen05.ld -> bias (broadcast loads) / scale / GELU in registers -> residual added from a tile the
 //             warp TMA-loaded two chunks earlier -> result written in place into the 128B-swizzled smem chunk -> one TMA
@@ -42,7 +47,10 @@ constexpr int CHUNK_BYTES = 32 * 128;         // 32 rows x 128 B (32 f32 or 64 f
 constexpr int EPI_BYTES = EPI_WARPS * EPI_BUFS * CHUNK_BYTES;   // 96 KB
 constexpr int BAR_BYTES = 512;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024 /*align slack*/;
-constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;
+constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;          // F16 weights (W tile by TMA)
+constexpr int DQ_WARPS = 4;
+constexpr int NUM_THREADS_Q = NUM_THREADS + 32 * DQ_WARPS;   // quantised weights: + decode warpgroup
+constexpr int WT_F16 = 1, WT_Q4_0 = 2, WT_Q8_0 = 8;          // ggml_type values
 constexpr int TMEM_COLS = 512;
 constexpr int UMMA_K = 16;
 
@@ -54,6 +62,8 @@ struct KParams {
     int scale_cols;
     float scale;
     int m_tiles, n_tiles;   // in units of 256 x 256
+    const uint8_t* wraw;    // quantised W: raw ggml blocks, row pitch wrow_bytes
+    int wrow_bytes;
 };
 
 __device__ __forceinline__ float gelu_tanh(float x) {
@@ -63,8 +73,58 @@ __device__ __forceinline__ float gelu_tanh(float x) {
     return __fdividef(x, 1.0f + e);
 }
 
-template <int EPI>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+// ---- ggml block decode helpers (ggml-common.h:144-148, :186-191; ggml-quants.c:1522-1540, :1616-1630)
+// four biased bytes -> two half2 holding (1024 + b) exactly (0x64xx is 1024 + xx in F16), then subtract the bias and scale
+__device__ __forceinline__ void dq4(uint32_t biased, __half2 bias, __half2 d2, uint32_t& o0, uint32_t& o1) {
+    const uint32_t lo = __byte_perm(biased, 0x64646464u, 0x4140);
+    const uint32_t hi = __byte_perm(biased, 0x64646464u, 0x4342);
+    __half2 a = __hmul2(__hsub2(*reinterpret_cast<const __half2*>(&lo), bias), d2);
+    __half2 b = __hmul2(__hsub2(*reinterpret_cast<const __half2*>(&hi), bias), d2);
+    o0 = *reinterpret_cast<uint32_t*>(&a);
+    o1 = *reinterpret_cast<uint32_t*>(&b);
+}
+
+template <int WT> struct DqTraits;
+template <> struct DqTraits<WT_Q8_0> { static constexpr int WORDS = 17; static constexpr int BLOCK_BYTES = 34; };
+template <> struct DqTraits<WT_Q4_0> { static constexpr int WORDS = 9;  static constexpr int BLOCK_BYTES = 18; };
+
+// decode the two blocks of one k-step (64 elements) of one W row into 32 packed half2 words
+template <int WT>
+__device__ __forceinline__ void decode_row(const uint32_t (&w)[DqTraits<WT>::WORDS], uint32_t (&out)[32]) {
+    if constexpr (WT == WT_Q8_0) {
+        // bytes: [d0:2][q0:32][d1:2][q1:32]  ->  w[0] = d0 | q0[0..1], w[8] = q0[30..31] | d1, w[9..16] = q1 (aligned)
+        const __half2 bias = __float2half2_rn(1152.0f);            // 1024 + 128
+        const __half2 d0 = __half2half2(__ushort_as_half(static_cast<unsigned short>(w[0] & 0xFFFF)));
+        const __half2 d1 = __half2half2(__ushort_as_half(static_cast<unsigned short>(w[8] >> 16)));
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const uint32_t q = __byte_perm(w[j], w[j + 1], 0x5432) ^ 0x80808080u;   // re-align block 0 by two bytes, bias to unsigned
+            dq4(q, bias, d0, out[2 * j], out[2 * j + 1]);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dq4(w[9 + j] ^ 0x80808080u, bias, d1, out[16 + 2 * j], out[16 + 2 * j + 1]);
+    } else {
+        // bytes: [d0:2][qs0:16][d1:2][qs1:16]; element j = low nibble of qs[j], element j+16 = high nibble of qs[j]
+        const __half2 bias = __float2half2_rn(1032.0f);            // 1024 + 8
+        const __half2 d0 = __half2half2(__ushort_as_half(static_cast<unsigned short>(w[0] & 0xFFFF)));
+        const __half2 d1 = __half2half2(__ushort_as_half(static_cast<unsigned short>(w[4] >> 16)));
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t q = __byte_perm(w[j], w[j + 1], 0x5432);
+            dq4(q & 0x0F0F0F0Fu, bias, d0, out[2 * j], out[2 * j + 1]);                  // elements 4j .. 4j+3
+            dq4((q >> 4) & 0x0F0F0F0Fu, bias, d0, out[8 + 2 * j], out[8 + 2 * j + 1]);   // elements 16+4j ..
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t q = w[5 + j];
+            dq4(q & 0x0F0F0F0Fu, bias, d1, out[16 + 2 * j], out[16 + 2 * j + 1]);
+            dq4((q >> 4) & 0x0F0F0F0Fu, bias, d1, out[24 + 2 * j], out[24 + 2 * j + 1]);
+        }
+    }
+}
+
+template <int EPI, int WT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WT == WT_F16 ? NUM_THREADS : NUM_THREADS_Q, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR, const KParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -93,7 +153,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         tma_prefetch_desc(&tmO);
         if constexpr (EPI == EPI_BIAS_RESID_F32) tma_prefetch_desc(&tmR);
         for (int s = 0; s < STAGES; ++s) {
-            mbar_init(&full_bar[s], 1);
+            mbar_init(&full_bar[s], WT == WT_F16 ? 1 : 1 + 2 * DQ_WARPS);   // producer's expect_tx (+ decode warps of both CTAs)
             mbar_init(&empty_bar[s], 1);
         }
         for (int s = 0; s < 2; ++s) {
@@ -124,10 +184,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sA = smem + stage * STAGE_BYTES;
                     uint8_t* sB = sA + A_BYTES;
-                    if (leader) mbar_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);   // bytes of both CTAs
+                    if (leader) mbar_expect_tx(&full_bar[stage], WT == WT_F16 ? 2 * STAGE_BYTES : 2 * A_BYTES);   // TMA bytes of both CTAs
                     const uint32_t full_leader = smem_u32(&full_bar[stage]) & kPeerBitMask;
                     tma_load_2d_cta2(sA, &tmA, full_leader, kb * BK, m0);
-                    tma_load_2d_cta2(sB, &tmB, full_leader, kb * BK, n0);
+                    if constexpr (WT == WT_F16) tma_load_2d_cta2(sB, &tmB, full_leader, kb * BK, n0);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -163,6 +223,49 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
         }
         __syncwarp();
+    } else if (WT != WT_F16 && warp >= 2 + EPI_WARPS) {
+        // ------------------------------------------------------------ in-kernel ggml block decode (warps 10..13, both CTAs)
+        if constexpr (WT != WT_F16) {
+            constexpr int WORDS = DqTraits<WT>::WORDS;
+            const int row = (warp - 2 - EPI_WARPS) * 32 + lane;            // row of this CTA's W half
+            const uint32_t row_off = static_cast<uint32_t>(row) * 128;
+            const uint32_t sw = static_cast<uint32_t>(row & 7);
+            const int kblocks = p.K / 32;                                   // ggml blocks per row
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+                const int n = (tile % p.n_tiles) * BN + static_cast<int>(cta_rank) * (BN / 2) + row;
+                const bool valid = n < p.N;
+                const uint32_t* wrow = reinterpret_cast<const uint32_t*>(p.wraw + static_cast<size_t>(valid ? n : 0) * p.wrow_bytes);
+                uint32_t cur[WORDS], nxt[WORDS];
+                auto fetch = [&](int kb, uint32_t (&dst)[WORDS]) {
+                    // two blocks = 2 * BLOCK_BYTES bytes, 4-byte aligned because K % 64 == 0; the second block may lie past K
+                    const bool two = 2 * kb + 1 < kblocks;
+                    const uint32_t* src = wrow + static_cast<size_t>(kb) * (2 * DqTraits<WT>::BLOCK_BYTES / 4);
+#pragma unroll
+                    for (int i = 0; i < WORDS; ++i) dst[i] = (valid && (two || i < WORDS / 2 + 1)) ? __ldg(src + i) : 0u;
+                };
+                fetch(0, cur);
+                for (int kb = 0; kb < nkb; ++kb) {
+                    if (kb + 1 < nkb) fetch(kb + 1, nxt);                    // one k-step ahead, overlaps the wait + decode below
+                    uint32_t o[32];
+                    decode_row<WT>(cur, o);
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sB = smem + stage * STAGE_BYTES + A_BYTES;
+#pragma unroll
+                    for (int c = 0; c < 8; ++c)
+                        *reinterpret_cast<uint4*>(sB + row_off + ((static_cast<uint32_t>(c) ^ sw) << 4)) =
+                            make_uint4(o[4 * c + 0], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
+                    fence_proxy_async_smem();                                // generic-proxy writes -> visible to the tensor core
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(&full_bar[stage], 0); // the leader's full barrier, from either CTA
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+#pragma unroll
+                    for (int i = 0; i < WORDS; ++i) cur[i] = nxt[i];
+                }
+            }
+            __syncwarp();
+        }
     } else {
         // ------------------------------------------------------------ epilogue (warps 2..9)
         const int ew = warp - 2;
@@ -360,12 +463,12 @@ bool make_tmap_2d(CUtensorMap* tm, const void* ptr, CUtensorMapDataType dt, size
 std::atomic<int> g_launches{0};
 int g_num_sms = 0;
 
-template <int EPI>
+template <int EPI, int WT>
 cudaError_t launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const CUtensorMap& tmR, const KParams& kp,
                    cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(gemm_kernel<EPI, WT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
         if (e != cudaSuccess) return e;
         configured = true;
     }
@@ -377,7 +480,7 @@ cudaError_t launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtenso
     const int tiles = kp.m_tiles * kp.n_tiles;
     const int max_clusters = g_num_sms / 2;
     const int clusters = tiles < max_clusters ? tiles : max_clusters;
-    gemm_kernel<EPI><<<2 * clusters, NUM_THREADS, SMEM_BYTES, st>>>(tmA, tmB, tmO, tmR, kp);
+    gemm_kernel<EPI, WT><<<2 * clusters, WT == WT_F16 ? NUM_THREADS : NUM_THREADS_Q, SMEM_BYTES, st>>>(tmA, tmB, tmO, tmR, kp);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return cudaGetLastError();
 }
@@ -394,7 +497,14 @@ cudaError_t gemm_f16_tcgen05(const GemmArgs& a, GemmEpilogue epi, cudaStream_t s
     const bool f16out = (epi == EPI_BIAS_F16 || epi == EPI_BIAS_GELU_F16);
     CUtensorMap tmA, tmB, tmO, tmR;
     if (!make_tmap_2d(&tmA, a.A, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, a.M, a.K, a.lda, BM, BK)) return cudaErrorInvalidValue;
-    if (!make_tmap_2d(&tmB, a.W, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, a.N, a.K, a.ldw, BN / 2, BK)) return cudaErrorInvalidValue;
+    const int wt = a.wtype == 0 ? WT_F16 : a.wtype;
+    if (wt != WT_F16 && wt != WT_Q8_0 && wt != WT_Q4_0) return cudaErrorInvalidValue;
+    if (wt == WT_F16) {
+        if (!make_tmap_2d(&tmB, a.W, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, a.N, a.K, a.ldw, BN / 2, BK)) return cudaErrorInvalidValue;
+    } else {
+        if (a.K % 64) return cudaErrorInvalidValue;     // two whole ggml blocks per k-step keep the raw reads 4-byte aligned
+        tmB = tmA;                                      // unused
+    }
     if (f16out) {
         if (!make_tmap_2d(&tmO, a.out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, a.M, a.N, a.ldo, 32, 64)) return cudaErrorInvalidValue;
     } else {
@@ -413,15 +523,24 @@ cudaError_t gemm_f16_tcgen05(const GemmArgs& a, GemmEpilogue epi, cudaStream_t s
     kp.scale_cols = a.scale_cols; kp.scale = a.scale;
     kp.m_tiles = (a.M + 2 * BM - 1) / (2 * BM);
     kp.n_tiles = (a.N + BN - 1) / BN;
+    kp.wraw = static_cast<const uint8_t*>(static_cast<const void*>(a.W));
+    kp.wrow_bytes = wt == WT_Q8_0 ? a.K / 32 * 34 : wt == WT_Q4_0 ? a.K / 32 * 18 : 0;
+    if (epi == EPI_BIAS_GELU_POS_F32 && !a.pos) return cudaErrorInvalidValue;
+#define Q2W_DISPATCH(E)                                                                 \
+    case E:                                                                             \
+        if (wt == WT_F16) return launch<E, WT_F16>(tmA, tmB, tmO, tmR, kp, st);         \
+        if (wt == WT_Q8_0) return launch<E, WT_Q8_0>(tmA, tmB, tmO, tmR, kp, st);       \
+        return launch<E, WT_Q4_0>(tmA, tmB, tmO, tmR, kp, st);
     switch (epi) {
-        case EPI_BIAS_F16:          return launch<EPI_BIAS_F16>(tmA, tmB, tmO, tmR, kp, st);
-        case EPI_BIAS_GELU_F16:     return launch<EPI_BIAS_GELU_F16>(tmA, tmB, tmO, tmR, kp, st);
-        case EPI_BIAS_RESID_F32:    return launch<EPI_BIAS_RESID_F32>(tmA, tmB, tmO, tmR, kp, st);
-        case EPI_BIAS_GELU_POS_F32:
-            if (!a.pos) return cudaErrorInvalidValue;
-            return launch<EPI_BIAS_GELU_POS_F32>(tmA, tmB, tmO, tmR, kp, st);
-        case EPI_BIAS_F32:          return launch<EPI_BIAS_F32>(tmA, tmB, tmO, tmR, kp, st);
+        Q2W_DISPATCH(EPI_BIAS_F16)
+        Q2W_DISPATCH(EPI_BIAS_GELU_F16)
+        Q2W_DISPATCH(EPI_BIAS_RESID_F32)
+        Q2W_DISPATCH(EPI_BIAS_F32)
+        case EPI_BIAS_GELU_POS_F32:     // conv stem only: its kernels are always F16 in the model file (vtype, :1543)
+            if (wt != WT_F16) return cudaErrorInvalidValue;
+            return launch<EPI_BIAS_GELU_POS_F32, WT_F16>(tmA, tmB, tmO, tmR, kp, st);
     }
+#undef Q2W_DISPATCH
     return cudaErrorInvalidValue;
 }
 

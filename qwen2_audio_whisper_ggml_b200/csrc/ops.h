@@ -20,7 +20,8 @@ enum GemmEpilogue : int {
 
 struct GemmArgs {
     const __half* A;  int lda;    // activations [M, K]
-    const __half* W;  int ldw;    // weights     [N, K]   (ggml mul_mat layout: ne0 = K contiguous)
+    const __half* W;  int ldw;    // weights     [N, K]   (ggml mul_mat layout: ne0 = K contiguous); raw ggml blocks if wtype is Q8_0 / Q4_0
+    int wtype;                    // 0 or 1 = F16 (TMA-loaded), 8 = Q8_0, 2 = Q4_0 (decoded inside the kernel; needs K % 64 == 0)
     int M, N, K;
     const float* bias;            // [N] or nullptr (treated as 0)
     void* out;        int ldo;    // [M, N] f16 or f32 depending on epilogue

@@ -64,6 +64,7 @@ _SIGS = {
     "q2w_device_count": (_i, []),
     "q2w_build_info": (C.c_char_p, []),
     "q2w_op_gemm": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _i, _i, _f, _vp]),
+    "q2w_op_gemm_q": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp, _i, _f, _vp]),
     "q2w_op_layernorm": (_i, [_vp, _vp, _vp, _vp, _i, _i, _f, _vp]),
     "q2w_op_pool_layernorm": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp]),
     "q2w_op_attention": (_i, [_vp, _vp, _i, _i, _i, _vp]),

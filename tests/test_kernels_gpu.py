@@ -64,6 +64,34 @@ def test_gemm(lib, M, N, K, epi):
     assert rel_l2(got, want) < tol, (rel_l2(got, want), max_abs(got, want))
 
 
+@pytest.mark.parametrize("ttype", [gq.GGML_TYPE_Q8_0, gq.GGML_TYPE_Q4_0])
+@pytest.mark.parametrize("M,N,K,epi", [(300, 384, 128, 0), (1500, 1280, 1280, 2), (2100, 5120, 1280, 1), (777, 1280, 5120, 2), (520, 136, 192, 4)])
+def test_gemm_in_kernel_dequant(lib, ttype, M, N, K, epi):
+    """W stays in ggml blocks; the GEMM's decode warpgroup must reproduce dequantize_row_* + F16 rounding exactly, so the result
+    equals the F16-weight GEMM on the decoded matrix bit for bit"""
+    rng = np.random.default_rng(M + N + K + ttype)
+    w = (rng.standard_normal((N, K)) / K ** 0.5).astype(np.float32)
+    w[1, :32] = 0.0
+    raw = gq.quantize(w, ttype).reshape(-1)
+    wdq = torch.from_numpy(gq.dequantize(raw, ttype, K).astype(np.float16)).cuda()
+    g = torch.Generator(device="cuda").manual_seed(3)
+    A = (torch.randn(M, K, device="cuda", generator=g) * 0.5).half()
+    bias = torch.randn(N, device="cuda", generator=g) * 0.1
+    d_raw = torch.from_numpy(raw.copy()).cuda()
+    dt = torch.half if epi in (0, 1) else torch.float32
+    resid = torch.randn(M, N, device="cuda", generator=g)
+    out_q = resid.clone().to(dt) if epi == 2 else torch.zeros(M, N, device="cuda", dtype=dt)
+    out_f = out_q.clone()
+    ck(lib.q2w_op_gemm_q(A.data_ptr(), K, d_raw.data_ptr(), ttype, M, N, K, bias.data_ptr(), out_q.data_ptr(), N, epi,
+                         out_q.data_ptr() if epi == 2 else None, N // 2 // 8 * 8, 0.125, None))
+    ck(lib.q2w_op_gemm(A.data_ptr(), K, wdq.data_ptr(), K, M, N, K, bias.data_ptr(), out_f.data_ptr(), N, epi,
+                       out_f.data_ptr() if epi == 2 else None, None, 0, N // 2 // 8 * 8, 0.125, None))
+    assert torch.equal(out_q, out_f)
+    want = A.float() @ wdq.float().t() + bias
+    if epi == 4:
+        assert rel_l2(out_q.cpu().numpy(), want.cpu().numpy()) < 2e-5
+
+
 def test_gemm_strided_operands(lib):
     """lda / ldw / ldo larger than the logical widths (views into wider buffers)"""
     M, N, K = 520, 256, 192
