@@ -252,3 +252,25 @@ def test_cli_matches_reference_printout(ref, tmp_path, capfd):
     want = rctx.get_embeddings().reshape(-1)[:20]
     assert got.shape == (20,) and np.abs(got - want).max() < 5e-3      # %.3f rounding + F16 tolerance
     rctx.free()
+
+
+def test_hf_qwen2_audio_encoder_checkpoint_through_engine():
+    """independent oracle: HF transformers' Qwen2AudioEncoder (tanh GELU) -> converter -> this library == HF's own forward"""
+    pytest.importorskip("transformers")
+    from test_convert_cpu import tiny_hf_encoder
+    from oracle import mel_np
+    from qwen2_audio_whisper_ggml_b200 import convert
+    enc = tiny_hf_encoder(1)
+    sd = dict(enc.state_dict())
+    hp = convert.hparams_from_state_dict(sd, n_head=2, n_vocab=64)
+    pcm = synth.synth_pcm(32000, seed=4)
+    for wt, tol in ((gq.GGML_TYPE_F16, 2e-3), (gq.GGML_TYPE_F32, 2e-3), (gq.GGML_TYPE_Q8_0, 3e-2)):
+        mf = convert.from_state_dict(sd, wt, hp)
+        ctx = Context.init_from_buffer(mfm.to_bytes(mf))
+        assert ctx.full(pcm) == 0
+        win = mel_np.window(ctx.get_mel(), 0, 100)
+        with torch.no_grad():
+            want = enc(torch.from_numpy(win)[None]).last_hidden_state[0].numpy()
+        got = ctx.get_embeddings()[0]
+        assert rel_l2(got, want) < tol, (gq.TYPE_NAMES[wt], rel_l2(got, want))
+        ctx.free()
