@@ -37,16 +37,21 @@ namespace {
 constexpr int BM = 128;            // rows per CTA (256 per pair)
 constexpr int BN = 256;            // columns per pair tile; each CTA stages BN/2 rows of W
 constexpr int BK = 64;
-constexpr int STAGES = 4;
+// smem budget (227 KB): F16-output epilogues need only 2 chunk buffers per warp (no residual prefetch) and get a 5-stage ring;
+// the residual epilogues keep 3 buffers (2 residual tiles in flight + 1 draining) and a 4-stage ring
+template <int EPI> struct Cfg {
+    static constexpr bool F16OUT = (EPI == EPI_BIAS_F16 || EPI == EPI_BIAS_GELU_F16);
+    static constexpr int STAGES = F16OUT ? 5 : 4;
+    static constexpr int EPI_BUFS = F16OUT ? 2 : 3;
+};
 constexpr int A_BYTES = BM * BK * 2;          // 16 KB
 constexpr int B_BYTES = (BN / 2) * BK * 2;    // 16 KB (this CTA's half of W)
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int EPI_WARPS = 8;
-constexpr int EPI_BUFS = 3;                   // per-warp rotation: load (2 chunks ahead) / compute in place / store draining
 constexpr int CHUNK_BYTES = 32 * 128;         // 32 rows x 128 B (32 f32 or 64 f16 columns)
-constexpr int EPI_BYTES = EPI_WARPS * EPI_BUFS * CHUNK_BYTES;   // 96 KB
 constexpr int BAR_BYTES = 512;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024 /*align slack*/;
+template <int EPI> constexpr int epi_bytes() { return EPI_WARPS * Cfg<EPI>::EPI_BUFS * CHUNK_BYTES; }   // 64 / 96 KB
+template <int EPI> constexpr int smem_bytes() { return Cfg<EPI>::STAGES * STAGE_BYTES + epi_bytes<EPI>() + BAR_BYTES + 1024 /*align slack*/; }
 constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;          // F16 weights (W tile by TMA)
 constexpr int DQ_WARPS = 4;
 constexpr int NUM_THREADS_Q = NUM_THREADS + 32 * DQ_WARPS;   // quantised weights: + decode warpgroup
@@ -127,6 +132,9 @@ template <int EPI, int WT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WT == WT_F16 ? NUM_THREADS : NUM_THREADS_Q, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR, const KParams p) {
+    constexpr int STAGES = Cfg<EPI>::STAGES;
+    constexpr int EPI_BUFS = Cfg<EPI>::EPI_BUFS;
+    constexpr int EPI_BYTES = epi_bytes<EPI>();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* epi_smem = smem + STAGES * STAGE_BYTES;
@@ -468,7 +476,7 @@ cudaError_t launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtenso
                    cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_kernel<EPI, WT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(gemm_kernel<EPI, WT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<EPI>());
         if (e != cudaSuccess) return e;
         configured = true;
     }
@@ -480,7 +488,7 @@ cudaError_t launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtenso
     const int tiles = kp.m_tiles * kp.n_tiles;
     const int max_clusters = g_num_sms / 2;
     const int clusters = tiles < max_clusters ? tiles : max_clusters;
-    gemm_kernel<EPI, WT><<<2 * clusters, WT == WT_F16 ? NUM_THREADS : NUM_THREADS_Q, SMEM_BYTES, st>>>(tmA, tmB, tmO, tmR, kp);
+    gemm_kernel<EPI, WT><<<2 * clusters, WT == WT_F16 ? NUM_THREADS : NUM_THREADS_Q, smem_bytes<EPI>(), st>>>(tmA, tmB, tmO, tmR, kp);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return cudaGetLastError();
 }
