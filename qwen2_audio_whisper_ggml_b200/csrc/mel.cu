@@ -37,6 +37,7 @@ constexpr int FPB = 16;                               // frames per block
 constexpr int SEG = (FPB - 1) * HOP + N_FFT;          // 2800 samples staged per block
 constexpr int ZPITCH = NZ + NZ / 8;                   // 225 float2 per frame (1 pad per 8 -> conflict-free radix-8 stores)
 constexpr int THREADS = 256;
+constexpr int P_BYTES = ((NBINS * FPB > SEG + N_FFT ? NBINS * FPB : SEG + N_FFT) * 4 + 15) / 16 * 16;   // max(s_p, s_x + s_hann)
 
 __host__ __device__ inline int zidx(int p) { return p + (p >> 3); }
 
@@ -82,11 +83,12 @@ mel_logpower_kernel(const float* __restrict__ filters, const int2* __restrict__ 
                     const int* __restrict__ n_samples_dev, int n_max, int n_frames, float* __restrict__ logmel,
                     int ld_frames, int* __restrict__ win_max_key) {
     extern __shared__ __align__(16) uint8_t smem_mel[];
+    // s_x and s_hann are dead after pass 1, so the power spectrum s_p reuses their bytes: 44.9 KB per block -> 5 blocks per SM
     float* s_x = reinterpret_cast<float*>(smem_mel);                 // [SEG]
     float* s_hann = s_x + SEG;                                       // [400]
-    float2* s_tw = reinterpret_cast<float2*>(s_hann + N_FFT);        // [400]
+    float* s_p = reinterpret_cast<float*>(smem_mel);                 // [NBINS][FPB]   (bin-major, frame-minor), aliases s_x | s_hann | pad
+    float2* s_tw = reinterpret_cast<float2*>(smem_mel + P_BYTES);    // [400]
     float2* s_z = s_tw + N_FFT;                                      // [FPB][ZPITCH]
-    float* s_p = reinterpret_cast<float*>(s_z + FPB * ZPITCH);       // [NBINS][FPB]   (bin-major, frame-minor)
     __shared__ float s_red[THREADS / 32];
 
     const int b = blockIdx.y;
@@ -107,18 +109,23 @@ mel_logpower_kernel(const float* __restrict__ filters, const int2* __restrict__ 
         return;
     }
 
-    // ---- stage the padded signal segment, window table and twiddles
-    for (int i = tid; i < SEG; i += THREADS) {
-        const long xi = x0 + i;
-        float v = 0.f;
-        if (xi < PAD) {
-            const long s = PAD - xi;             // reflect: x[i] = pcm[200 - i]
-            if (s < n) v = __ldg(pw + s);
-        } else {
-            const long s = xi - PAD;
-            if (s < n) v = __ldg(pw + s);
+    // ---- stage the padded signal segment, window table and twiddles.  All loads of a thread are issued before its stores
+    //      (round-1 ncu: the one-load-one-store loop spent 31 % of the kernel's stall samples waiting on its own LDG)
+    {
+        constexpr int PER_THREAD = (SEG + THREADS - 1) / THREADS;   // 11
+        float v[PER_THREAD];
+#pragma unroll
+        for (int it = 0; it < PER_THREAD; ++it) {
+            const int i = tid + it * THREADS;
+            const long xi = x0 + i;
+            const long sidx = xi < PAD ? PAD - xi : xi - PAD;        // reflect: x[i] = pcm[200 - i]
+            v[it] = (i < SEG && sidx < n) ? __ldg(pw + sidx) : 0.f;
         }
-        s_x[i] = v;
+#pragma unroll
+        for (int it = 0; it < PER_THREAD; ++it) {
+            const int i = tid + it * THREADS;
+            if (i < SEG) s_x[i] = v[it];
+        }
     }
     for (int i = tid; i < N_FFT; i += THREADS) {
         s_hann[i] = hann_g[i];
@@ -258,8 +265,7 @@ mel_normalize_kernel(float* __restrict__ mel, int ld_frames, int n_frames, int n
     }
 }
 
-constexpr size_t MEL_SMEM = sizeof(float) * (SEG + N_FFT) + sizeof(float2) * (N_FFT + FPB * ZPITCH) +
-                            sizeof(float) * (NBINS * FPB);
+constexpr size_t MEL_SMEM = P_BYTES + sizeof(float2) * (N_FFT + FPB * ZPITCH);
 
 }  // namespace
 
