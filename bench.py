@@ -165,9 +165,19 @@ def main():
         raise SystemExit("bench.py: no CUDA device (there is no CPU fallback for the product arm; use --impl reference)")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        # stdout carries exactly one JSON line: NCCL's version / debug banner (NCCL_DEBUG is set on the GPU boxes) goes to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # stdout carries exactly one JSON line: NCCL prints its version banner to stdout (NCCL_DEBUG is set on the GPU boxes), so
+        # fd 1 points at stderr while the communicator is created
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
     lib = L.load_library()
     api.log_set(lambda lvl, txt: None)
 
@@ -253,10 +263,9 @@ def main():
     #      the timed region -- SURVEY 8(e): "NCCL only to gather embeddings when a caller asks for them on one device")
     gather_ms = None
     if world > 1:
-        emb = torch.empty((B, 750, 1280), dtype=torch.float32, device="cuda")
-        step_device()
-        torch.cuda.cudart().cudaMemcpy(emb.data_ptr(), ctx.embeddings_device_ptr(), emb.numel() * 4, 3)   # cudaMemcpyDeviceToDevice
+        emb = out_host.cuda()                       # this rank's embeddings of the last end-to-end step
         parts = [torch.empty_like(emb) for _ in range(world)] if rank == 0 else None
+        dist.gather(emb, parts, dst=0)              # first use builds NCCL's p2p channels; time the second
         barrier()
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         g0.record()
