@@ -142,8 +142,12 @@ def main():
     if a.impl == "reference":
         if rank != 0:
             return
-        mb = build_model_bytes(a.wtype)
-        times = run_reference(mb, a.steps, a.warmup, threads)
+        try:
+            mb = build_model_bytes(a.wtype)
+            times = run_reference(mb, a.steps, a.warmup, threads)
+        except Exception as ex:   # oracle/_ref not shipped / wrong ISA: say so in one line, exit 0 (driver contract)
+            print(json.dumps({"impl": "reference", "unavailable": f"{type(ex).__name__}: {ex}"[:300]}))
+            return
         sec = statistics.median(times)
         val = WINDOW_S / sec
         sample = f"1 x 30 s window per step ({a.steps} steps, p50), {a.wtype} weights, n_threads={threads}"

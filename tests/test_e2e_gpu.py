@@ -274,3 +274,49 @@ def test_hf_qwen2_audio_encoder_checkpoint_through_engine():
         got = ctx.get_embeddings()[0]
         assert rel_l2(got, want) < tol, (gq.TYPE_NAMES[wt], rel_l2(got, want))
         ctx.free()
+
+
+def test_init_with_custom_loader_callbacks():
+    """whisper_init_with_params(loader): read / eof / close are invoked synchronously and close is always called (src:3111-3137)"""
+    import ctypes as C
+    w = api.wlib()
+    buf = mfm.to_bytes(synth.synth_model(synth.TINY_HPARAMS, gq.GGML_TYPE_Q4_0, seed=1))
+    state = {"off": 0, "closed": 0, "hit_end": False}
+
+    class Loader(C.Structure):
+        _fields_ = [("context", C.c_void_p), ("read", C.CFUNCTYPE(C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t)),
+                    ("eof", C.CFUNCTYPE(C.c_bool, C.c_void_p)), ("close", C.CFUNCTYPE(None, C.c_void_p))]
+
+    def rd(ctx, out, n):
+        k = min(n, len(buf) - state["off"])
+        if k < n:
+            state["hit_end"] = True
+        C.memmove(out, buf[state["off"]:state["off"] + k], k)
+        state["off"] += k
+        return k
+
+    ld = Loader(None, Loader._fields_[1][1](rd), Loader._fields_[2][1](lambda c: state["hit_end"]),
+                Loader._fields_[3][1](lambda c: state.__setitem__("closed", state["closed"] + 1)))
+    w.whisper_init_with_params.restype = C.c_void_p
+    w.whisper_init_with_params.argtypes = [C.POINTER(Loader), api.ContextParams]
+    h = w.whisper_init_with_params(C.byref(ld), api.default_context_params())
+    assert h and state["closed"] == 1 and state["off"] == len(buf)
+    ctx = Context(h)
+    assert ctx.model_n("ftype") == 2 and ctx.model_n("n_audio_layer") == 2
+    g = np.load(os.path.join(GOLD, "tiny_q4_0.npz"))
+    assert ctx.full(synth.synth_pcm(32000, seed=3)) == 0
+    assert rel_l2(ctx.get_embeddings()[0], g["emb"]) < TOL["q4_0"]["rel_l2"]
+    ctx.free()
+    # a loader that fails mid-way still gets closed, and init returns NULL
+    state.update(off=0, closed=0, hit_end=False)
+    short = buf[: len(buf) // 2]
+    def rd2(ctx, out, n):
+        k = min(n, len(short) - state["off"])
+        if k < n:
+            state["hit_end"] = True
+        C.memmove(out, short[state["off"]:state["off"] + k], k)
+        state["off"] += k
+        return k
+    ld2 = Loader(None, Loader._fields_[1][1](rd2), ld.eof, ld.close)
+    assert not w.whisper_init_with_params(C.byref(ld2), api.default_context_params())
+    assert state["closed"] == 1
