@@ -94,6 +94,10 @@ Q2W_API int  q2w_encode_batch_host(q2w_state* s, const float* pcm_host, size_t s
 Q2W_API int  q2w_encode_batch_device(q2w_state* s, const float* pcm_dev, size_t stride, const int32_t* n_samples_host,
                                      int B);
 
+/* Whole-file streaming: n windows of the state's (globally normalised) mel, starting at the given frame offsets,
+ * encoded as one batch -- the batched form of n x whisper_full(ctx, {offset_ms}, NULL, 0)  (:2349-2369). */
+Q2W_API int  q2w_encode_offsets(q2w_state* s, const int32_t* mel_offsets, int n, float* out_host);
+
 /* embeddings of the last encode / encode_batch (replaces the D2H in whisper_print_emb_enc :4196) */
 Q2W_API int  q2w_embd_dims(const q2w_state* s, int* n_windows, int* n_out, int* n_state);
 Q2W_API int  q2w_get_embeddings(q2w_state* s, float* out_host, size_t offset_floats, size_t n_floats);

@@ -204,6 +204,9 @@ WHISPER_API int whisper_get_mel(struct whisper_context * ctx, float * dst, size_
  * set once with whisper_set_max_batch (default 16). */
 WHISPER_API int whisper_encode_batch(struct whisper_context * ctx, const float * samples, size_t stride, const int32_t * n_samples, int n_windows, float * dst);
 WHISPER_API int whisper_encode_batch_device(struct whisper_context * ctx, const float * samples_dev, size_t stride, const int32_t * n_samples, int n_windows);
+/* whole-file streaming: after ONE whisper_pcm_to_mel over the full audio (global normalisation), encode n windows starting at the
+ * given mel-frame offsets (offset_ms / 10) as a batch == n x whisper_full(ctx, {offset_ms}, NULL, 0) of the reference */
+WHISPER_API int whisper_encode_offsets(struct whisper_context * ctx, const int32_t * mel_offsets, int n_windows, float * dst);
 WHISPER_API int whisper_set_max_batch(struct whisper_context * ctx, int max_batch);
 /* the underlying C-ABI state handle (q2w_state*, include/q2w_b200.h) for callers that need streams / device pointers */
 WHISPER_API void * whisper_q2w_state(struct whisper_context * ctx);

@@ -76,6 +76,7 @@ _WSIGS = {
     "whisper_encode_batch": (_i, [_vp, _vp, _sz, _vp, _i, _vp]),
     "whisper_encode_batch_device": (_i, [_vp, _vp, _sz, _vp, _i]),
     "whisper_set_max_batch": (_i, [_vp, _i]),
+    "whisper_encode_offsets": (_i, [_vp, _vp, _i, _vp]),
     "whisper_q2w_state": (_vp, [_vp]),
 }
 _bound = False
@@ -242,6 +243,20 @@ class Context:
         ns = np.full(nw, win, dtype=np.int32)
         ns[-1] = s.size - (nw - 1) * win
         return self.encode_batch(padded, ns, out=out)
+
+    def encode_stream(self, samples, hop_frames: int | None = None) -> np.ndarray:
+        """Whole-file streaming: ONE mel over the full audio (global normalisation, like the reference's whisper_pcm_to_mel),
+        then every window starting at k * hop_frames (default: 2 * n_audio_ctx, i.e. back-to-back 30 s windows) as one batch."""
+        if self.pcm_to_mel(samples) != 0:
+            raise _l.Q2WError(-1, "whisper_pcm_to_mel failed")
+        win = 2 * self.model_n("n_audio_ctx")
+        hop = hop_frames or win
+        n_org = self.n_len()
+        offs = np.arange(0, max(n_org, 1), hop, dtype=np.int32)
+        out = np.empty((offs.size, self.model_n("n_audio_ctx") // 2, self.model_n("n_audio_state")), dtype=np.float32)
+        if wlib().whisper_encode_offsets(self._h, offs.ctypes.data, offs.size, out.ctypes.data) != 0:
+            raise _l.Q2WError(-1, "whisper_encode_offsets failed (see log)")
+        return out
 
     def encode_batch_device(self, dev_ptr: int, stride: int, B: int, n_samples=None) -> int:
         ns = None if n_samples is None else np.ascontiguousarray(n_samples, dtype=np.int32)

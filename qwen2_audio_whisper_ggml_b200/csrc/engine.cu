@@ -657,6 +657,37 @@ int q2w_encode(q2w_state* s, int mel_offset) {
     return Q2W_OK;
 }
 
+// Whole-file streaming semantics: the state's mel was computed ONCE over the full PCM (global max, like
+// whisper_pcm_to_mel), and n windows starting at the given frame offsets are encoded as one batch -- the batched form of calling
+// whisper_full(ctx, {offset_ms}, NULL, 0) n times (src/qwen2-whisper.cpp:2349-2369: the mel is only recomputed when n_samples > 0).
+int q2w_encode_offsets(q2w_state* s, const int32_t* mel_offsets, int n, float* out_host) {
+    if (!s || !mel_offsets || n <= 0) return fail(Q2W_E_INVALID, "bad argument");
+    if (!s->api_mel || s->api_n_len <= 0) return fail(Q2W_E_INVALID, "no mel in this state: call q2w_pcm_to_mel or q2w_set_mel first");
+    for (int i = 0; i < n; ++i)
+        if (mel_offsets[i] < 0) return fail(Q2W_E_INVALID, "negative mel offset");
+    CK(cudaSetDevice(s->m->device));
+    const int64_t t0 = now_us();
+    int rc = ensure_emb(s, n);
+    if (rc) return rc;
+    const size_t a1_per_window = static_cast<size_t>(s->T2) * 3 * s->n_mel;
+    const size_t out_per_window = static_cast<size_t>(s->T / 2) * s->D;
+    for (int w0 = 0; w0 < n; w0 += s->max_batch) {
+        const int Bm = std::min(s->max_batch, n - w0);
+        for (int b = 0; b < Bm; ++b)   // window slice + zero fill past n_len + im2col, one launch per window (same mel, different offset)
+            CKL(mel_to_conv1_operand(s->api_mel, s->api_ld, s->api_n_len, s->n_mel, nullptr, 0, mel_offsets[w0 + b], s->T2, 1,
+                                     s->att + static_cast<size_t>(b) * a1_per_window, s->stream));
+        if ((rc = forward_from_a1(s, Bm, w0))) return rc;
+        if (out_host)
+            CK(cudaMemcpyAsync(out_host + static_cast<size_t>(w0) * out_per_window, s->emb + static_cast<size_t>(w0) * out_per_window,
+                               static_cast<size_t>(Bm) * out_per_window * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+    }
+    CK(cudaStreamSynchronize(s->stream));
+    s->emb_windows = n;
+    s->t_encode_us += now_us() - t0;
+    s->n_encode += n;
+    return Q2W_OK;
+}
+
 static int encode_batch_impl(q2w_state* s, const float* pcm, bool pcm_on_host, size_t stride, const int32_t* n_samples, int B,
                              float* out_host) {
     if (!s || !pcm || B <= 0) return fail(Q2W_E_INVALID, "bad argument");

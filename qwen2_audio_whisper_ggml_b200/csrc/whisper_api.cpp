@@ -593,6 +593,14 @@ int whisper_encode_batch_device(struct whisper_context* ctx, const float* sample
     }
     return 0;
 }
+int whisper_encode_offsets(struct whisper_context* ctx, const int32_t* mel_offsets, int n_windows, float* dst) {
+    if (!ctx || !ctx->state) return -1;
+    if (q2w_encode_offsets(ctx->state->qs, mel_offsets, n_windows, dst) != Q2W_OK) {
+        LOG_ERROR("%s: failed to encode: %s\n", __func__, q2w_last_error());
+        return -1;
+    }
+    return 0;
+}
 void* whisper_q2w_state(struct whisper_context* ctx) { return (ctx && ctx->state) ? ctx->state->qs : nullptr; }
 
 }  // extern "C"

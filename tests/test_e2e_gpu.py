@@ -320,3 +320,28 @@ def test_init_with_custom_loader_callbacks():
     ld2 = Loader(None, Loader._fields_[1][1](rd2), ld.eof, ld.close)
     assert not w.whisper_init_with_params(C.byref(ld2), api.default_context_params())
     assert state["closed"] == 1
+
+
+def test_whole_file_streaming_matches_reference_offsets(ref):
+    """one globally normalised mel over a long clip, all sliding windows as one batch ==
+    the reference's whisper_full(n_samples > 0) followed by whisper_full(NULL, 0, offset_ms = k * hop)"""
+    ctx, buf = tiny_ctx("f16", seed=5)
+    rctx = ref.RefContext(buf)
+    win_frames = 200
+    pcm = synth.synth_pcm(7 * 16000 + 777, seed=31, kind="chirp")          # 7.05 s -> 4 windows of 2 s, the last ragged
+    pcm[5 * 16000:] *= 0.01                                                 # quiet tail: global vs per-window normalisation differ here
+    out = ctx.encode_stream(pcm)
+    assert out.shape[0] == 4
+    assert rctx.full(pcm) == 0                                              # computes the mel once + window 0
+    for k in range(4):
+        if k:
+            assert rctx.full(None, offset_ms=k * win_frames * 10) == 0     # mel NOT recomputed (n_samples == 0)
+        assert rel_l2(out[k], rctx.get_embeddings()) < TOL["f16"]["rel_l2"], k
+    # per-window normalisation (encode_long) must differ on the quiet tail, or this test proves nothing
+    per_window = ctx.encode_long(pcm)
+    assert rel_l2(per_window[3], out[3]) > 1e-2
+    # half-window hop: 50 % overlap
+    out2 = ctx.encode_stream(pcm, hop_frames=100)
+    assert out2.shape[0] == 8 and np.array_equal(out2[0], out[0]) and np.array_equal(out2[2], out[1])
+    ctx.free()
+    rctx.free()
