@@ -20,6 +20,7 @@
 //               the magnitude of P (<= 256 in F16), and the final division by the row sum uses the same reference point.
 // Registers are rebalanced with setmaxnreg (producer/MMA warpgroup 56, softmax warpgroup 200).
 #include "ops.h"
+#include "launch.cuh"
 #include "ptx.cuh"
 
 #include <mutex>
@@ -119,6 +120,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm, __half* __restrict__
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();                  // the QKV GEMM's output is visible from here on; the prologue above overlapped its tail
+    pdl_launch_dependents();
 
     if (warp < 4) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
@@ -334,8 +337,7 @@ cudaError_t attention_f16_tcgen05(const __half* qkv, __half* out, int B, int T, 
         configured = true;
     }
     dim3 grid((T + BQ - 1) / BQ, H, B);
-    attention_tc_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(tm, out, T, D);
-    return cudaGetLastError();
+    return launch_pdl(attention_tc_kernel, grid, dim3(THREADS), SMEM_BYTES, st, tm, out, T, D);
 }
 
 }  // namespace q2w

@@ -7,7 +7,9 @@
 //   ggml_pool_1d(AVG,2,2,0)  ggml/src/ggml.c:15077-15125  (src/qwen2-whisper.cpp:2160-2171)
 //   im2col_f32               ggml/src/ggml.c:14717        column index = ic*K + k, zero padding
 //   dequantize_row_q8_0      ggml/src/ggml-quants.c:1616 ; dequantize_row_q4_0 :1522 ; block layouts ggml-common.h:144,186
+#include "launch.cuh"
 #include "ops.h"
+#include "ptx.cuh"
 
 #include <cstdint>
 
@@ -28,6 +30,8 @@ template <bool POOL, typename OutT>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                  OutT* __restrict__ y, int rows_out, int D, float eps, int T /*POOL: input rows per window*/) {
+    pdl_wait();               // predecessor grid complete + visible (launch.cuh)
+    pdl_launch_dependents();
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (warp >= rows_out) return;
@@ -101,6 +105,8 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, c
 __global__ void __launch_bounds__(256)
 conv1_operand_kernel(const float* __restrict__ mel, int ld_frames, int n_frames_valid, int n_mel,
                      const float* __restrict__ win_max, int normalise, int offset, int n_ctx2, __half* __restrict__ A1) {
+    pdl_wait();               // predecessor grid complete + visible (launch.cuh)
+    pdl_launch_dependents();
     extern __shared__ float s_mel[];  // [n_mel][35]
     const int b = blockIdx.y;
     const int t0 = blockIdx.x * 32;
@@ -137,6 +143,8 @@ conv1_operand_kernel(const float* __restrict__ mel, int ld_frames, int n_frames_
 // conv2 operand: A2[(b*T + t)][ic*3 + k] = h1[(b*T2 + 2t + k - 1)][ic], zero outside [0, T2).  8 outputs (16 B) per thread.
 __global__ void __launch_bounds__(256)
 conv2_im2col_kernel(const __half* __restrict__ h1, __half* __restrict__ A2, int B, int T2, int C) {
+    pdl_wait();               // predecessor grid complete + visible (launch.cuh)
+    pdl_launch_dependents();
     const int T = T2 >> 1;
     const int ncol = 3 * C;
     const int vec_per_row = ncol >> 3;
@@ -162,6 +170,8 @@ conv2_im2col_kernel(const __half* __restrict__ h1, __half* __restrict__ A2, int 
 // ggml block decode, one thread per 32-element block (weights are L2-resident, output 64 B / thread)
 __global__ void __launch_bounds__(256)
 dequant_q8_0_kernel(const uint8_t* __restrict__ src, __half* __restrict__ dst, size_t nblocks) {
+    pdl_wait();               // predecessor grid complete + visible (launch.cuh)
+    pdl_launch_dependents();
     const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= nblocks) return;
     const uint16_t* p = reinterpret_cast<const uint16_t*>(src + i * 34);  // {f16 d; int8 qs[32]}, 2-byte aligned
@@ -180,6 +190,8 @@ dequant_q8_0_kernel(const uint8_t* __restrict__ src, __half* __restrict__ dst, s
 
 __global__ void __launch_bounds__(256)
 dequant_q4_0_kernel(const uint8_t* __restrict__ src, __half* __restrict__ dst, size_t nblocks) {
+    pdl_wait();               // predecessor grid complete + visible (launch.cuh)
+    pdl_launch_dependents();
     const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= nblocks) return;
     const uint16_t* p = reinterpret_cast<const uint16_t*>(src + i * 18);  // {f16 d; u8 qs[16]}
@@ -201,6 +213,8 @@ dequant_q4_0_kernel(const uint8_t* __restrict__ src, __half* __restrict__ dst, s
 
 __global__ void __launch_bounds__(256)
 f32_to_f16_kernel(const float* __restrict__ src, __half* __restrict__ dst, size_t n) {
+    pdl_wait();               // predecessor grid complete + visible (launch.cuh)
+    pdl_launch_dependents();
     for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
          i += static_cast<size_t>(gridDim.x) * blockDim.x)
         dst[i] = __float2half_rn(src[i]);
@@ -213,8 +227,7 @@ cudaError_t layernorm_f32_to_f16(const float* x, const float* gamma, const float
     if (D % 4 || D > LN_MAX_VPL * 128 || M <= 0) return cudaErrorInvalidValue;
     const int warps_per_block = 8;
     const int grid = (M + warps_per_block - 1) / warps_per_block;
-    layernorm_kernel<false, __half><<<grid, warps_per_block * 32, 0, st>>>(x, gamma, beta, y, M, D, eps, 0);
-    return cudaGetLastError();
+    return launch_pdl(layernorm_kernel<false, __half>, dim3(grid), dim3(warps_per_block * 32), 0, st, x, gamma, beta, y, M, D, eps, 0);
 }
 
 cudaError_t pool2_layernorm_f32(const float* x, const float* gamma, const float* beta, float* y, int B, int T, int D,
@@ -223,8 +236,7 @@ cudaError_t pool2_layernorm_f32(const float* x, const float* gamma, const float*
     const int rows_out = B * (T / 2);
     const int warps_per_block = 8;
     const int grid = (rows_out + warps_per_block - 1) / warps_per_block;
-    layernorm_kernel<true, float><<<grid, warps_per_block * 32, 0, st>>>(x, gamma, beta, y, rows_out, D, eps, T);
-    return cudaGetLastError();
+    return launch_pdl(layernorm_kernel<true, float>, dim3(grid), dim3(warps_per_block * 32), 0, st, x, gamma, beta, y, rows_out, D, eps, T);
 }
 
 cudaError_t mel_to_conv1_operand(const float* mel, int ld_frames, int n_frames_valid, int n_mel, const float* win_max,
@@ -232,9 +244,8 @@ cudaError_t mel_to_conv1_operand(const float* mel, int ld_frames, int n_frames_v
     if (B <= 0 || n_ctx2 <= 0 || n_mel <= 0 || (3 * n_mel) % 8) return cudaErrorInvalidValue;
     dim3 grid((n_ctx2 + 31) / 32, B);
     const size_t smem = static_cast<size_t>(n_mel) * 35 * sizeof(float);
-    conv1_operand_kernel<<<grid, 256, smem, st>>>(mel, ld_frames, n_frames_valid, n_mel, win_max, normalise, offset,
-                                                  n_ctx2, A1);
-    return cudaGetLastError();
+    return launch_pdl(conv1_operand_kernel, grid, dim3(256), smem, st, mel, ld_frames, n_frames_valid, n_mel, win_max, normalise, offset,
+                      n_ctx2, A1);
 }
 
 cudaError_t conv2_im2col(const __half* h1, __half* A2, int B, int T2, int C, cudaStream_t st) {
@@ -242,8 +253,7 @@ cudaError_t conv2_im2col(const __half* h1, __half* A2, int B, int T2, int C, cud
     const size_t total = static_cast<size_t>(B) * (T2 / 2) * (3 * C / 8);
     size_t blocks = (total + 255) / 256;
     if (blocks > 148 * 32) blocks = 148 * 32;
-    conv2_im2col_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(h1, A2, B, T2, C);
-    return cudaGetLastError();
+    return launch_pdl(conv2_im2col_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, st, h1, A2, B, T2, C);
 }
 
 cudaError_t dequant_to_f16(const void* src, int ggml_type, __half* dst, size_t rows, int K, cudaStream_t st) {
@@ -251,14 +261,13 @@ cudaError_t dequant_to_f16(const void* src, int ggml_type, __half* dst, size_t r
     const size_t nblocks = rows * static_cast<size_t>(K / 32);
     const unsigned grid = static_cast<unsigned>((nblocks + 255) / 256);
     switch (ggml_type) {
-        case 8: dequant_q8_0_kernel<<<grid, 256, 0, st>>>(static_cast<const uint8_t*>(src), dst, nblocks); break;
-        case 2: dequant_q4_0_kernel<<<grid, 256, 0, st>>>(static_cast<const uint8_t*>(src), dst, nblocks); break;
+        case 8: return launch_pdl(dequant_q8_0_kernel, dim3(grid), dim3(256), 0, st, static_cast<const uint8_t*>(src), dst, nblocks);
+        case 2: return launch_pdl(dequant_q4_0_kernel, dim3(grid), dim3(256), 0, st, static_cast<const uint8_t*>(src), dst, nblocks);
         case 0: {
             const size_t n = rows * static_cast<size_t>(K);
             size_t blocks = (n + 255) / 256;
             if (blocks > 148 * 32) blocks = 148 * 32;
-            f32_to_f16_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(static_cast<const float*>(src), dst, n);
-            break;
+            return launch_pdl(f32_to_f16_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, st, static_cast<const float*>(src), dst, n);
         }
         default: return cudaErrorInvalidValue;
     }

@@ -25,6 +25,7 @@
 //             the TMA unit on store and zero-filled on load.  (Round-1 profiles: the per-element LDG/STG epilogue spent
 //             ~45 % of its issue slots on 64-bit address math and kept the K = 1280 GEMMs at 45-55 % tensor-pipe activity.)
 #include "ops.h"
+#include "launch.cuh"
 #include "ptx.cuh"
 
 #include <atomic>
@@ -179,6 +180,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     cluster_sync_all();          // barrier inits of both CTAs visible before any remote arrive / multicast
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();                  // everything above overlapped the previous kernel's tail; from here on its output is visible
+    pdl_launch_dependents();
 
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer (both CTAs)
@@ -488,9 +491,9 @@ cudaError_t launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtenso
     const int tiles = kp.m_tiles * kp.n_tiles;
     const int max_clusters = g_num_sms / 2;
     const int clusters = tiles < max_clusters ? tiles : max_clusters;
-    gemm_kernel<EPI, WT><<<2 * clusters, WT == WT_F16 ? NUM_THREADS : NUM_THREADS_Q, smem_bytes<EPI>(), st>>>(tmA, tmB, tmO, tmR, kp);
     g_launches.fetch_add(1, std::memory_order_relaxed);
-    return cudaGetLastError();
+    return launch_pdl(gemm_kernel<EPI, WT>, dim3(2 * clusters), dim3(WT == WT_F16 ? NUM_THREADS : NUM_THREADS_Q), smem_bytes<EPI>(), st, tmA, tmB,
+                      tmO, tmR, kp);
 }
 
 }  // namespace

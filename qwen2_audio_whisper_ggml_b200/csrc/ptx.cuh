@@ -201,4 +201,12 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N, int a_mn_maj
            (static_cast<uint32_t>(M >> 4) << 24);
 }
 
+
+// Programmatic dependent launch: a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization starts while its
+// predecessor in the stream is still running; everything before pdl_wait() (barrier init, TMEM alloc, descriptor prefetch)
+// overlaps the predecessor's tail, nothing after it can see stale memory. EVERY thread of EVERY CTA calls pdl_wait() before
+// its first global access, so "this grid completed" always implies "its predecessor completed".
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 }  // namespace q2w
