@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- audio-seconds/second of the mel + encoder hot path (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--wtype f16|q8_0|q4_0] [--windows B] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--wtype f16|q8_0|q4_0] [--windows B | --total-windows W] [--impl reference]
 
 A step = one pass of the hot path (PCM -> log-mel -> conv stem -> 32 encoder blocks -> pool -> LN) over one batch of
 B synthetic 30 s windows per GPU (default B = 64, F16: BASELINE.json configs[1]).  One process per GPU; for N > 1 launch
@@ -123,6 +123,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--wtype", default="f16", choices=["f16", "q8_0", "q4_0"])
     ap.add_argument("--windows", type=int, default=64, help="30 s windows per GPU per step")
+    ap.add_argument("--total-windows", type=int, default=0, help="strong scaling: this many windows in total, sharded over the ranks "
+                    "(BASELINE configs[2]/[3]: 256; configs[4], 1 h of audio: 120)")
     ap.add_argument("--max-batch", type=int, default=0, help="windows per micro-batch (default: = --windows)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -133,9 +135,20 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     threads = a.cpu_threads or (os.cpu_count() or 1)
-    workload = (f"BASELINE configs[1]: Qwen2-Audio encoder {a.wtype.upper()} (32L, d=1280, 20 heads, 128 mel), "
-                f"{a.windows} x 30 s windows per GPU, mel + encoder")
+    scaling = "weak"
+    if a.total_windows:
+        from qwen2_audio_whisper_ggml_b200.parallel import shard_bounds
+        lo, hi = shard_bounds(a.total_windows, rank, world)
+        a.windows = hi - lo
+        scaling = "strong"
+    if a.total_windows:
+        workload = (f"BASELINE configs[2]-[4] shape: Qwen2-Audio encoder {a.wtype.upper()} (32L, d=1280, 20 heads, 128 mel), {a.total_windows} x 30 s windows "
+                    f"({a.total_windows * 30 / 3600:.2f} h of audio) sharded over {world} GPU(s), mel + encoder")
+    else:
+        workload = (f"BASELINE configs[1]: Qwen2-Audio encoder {a.wtype.upper()} (32L, d=1280, 20 heads, 128 mel), "
+                    f"{a.windows} x 30 s windows per GPU, mel + encoder")
     config = {"workload": workload, "windows_per_gpu": a.windows, "weights": a.wtype, "sharding": f"dp{world} (independent windows, replicated weights, no collective)",
+              "total_windows": a.total_windows or a.windows * world,
               "l2": "no explicit flush: each step streams ~2.7 GB of activations + 1.26 GB of weights, >> 126 MB L2"}
 
     # ------------------------------------------------------------------ reference arm
@@ -284,7 +297,7 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms, e2e_s = float(t[0]), float(t[1])
-    total_audio = WINDOW_S * B * world * a.steps
+    total_audio = WINDOW_S * (a.total_windows or B * world) * a.steps
     value = total_audio / (dev_ms / 1e3)
     e2e_value = total_audio / e2e_s
 
@@ -321,7 +334,7 @@ def main():
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-                "ms_per_step": dev_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
+                "ms_per_step": dev_ms / a.steps, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f16",
                 "data": "synthetic", "config": config, "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(host.numel() * 4), "d2h_bytes_per_step": int(out_host.numel() * 4),
                         "ms_per_step": 1e3 * e2e_s / a.steps},
