@@ -23,6 +23,7 @@
 #include "launch.cuh"
 #include "ptx.cuh"
 
+#include <cstdlib>
 #include <mutex>
 
 namespace q2w {
@@ -38,6 +39,7 @@ constexpr int TMEM_COLS = 256;
 constexpr int S_COL = 0, O_COL = 128, P_COL = 192;   // S f32 [0,128) | O f32 [128,192) | P f16x2 [192,256)
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float RESCALE_THRESHOLD = 8.0f;       // log2 units
+constexpr int ATT_POLY_DEFAULT = 0;
 
 // MN-major operand tile written by TMA with SWIZZLE_128B: each K row is 128 B (64 f16 along N), 8-row groups 1024 B apart
 __device__ __forceinline__ uint64_t make_sw128_mnmajor_desc(uint32_t smem_addr) {
@@ -54,6 +56,55 @@ __device__ __forceinline__ float ex2(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
+}
+
+// ---- packed FP32x2 arithmetic (FFMA2 / FADD2: one issue slot per two elements) and the 3-input FMNMX3
+__device__ __forceinline__ uint64_t pack2(float a, float b) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ uint64_t add2_rm(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("add.rm.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ float max3(float a, float b, float c) {
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+// 2^x for a pair of log2-domain scores WITHOUT the MUFU: x = n + f (n = floor via the 1.5*2^23 magic add rounded down, f in [0,1)),
+// 2^f by a degree-3 minimax polynomial (max rel. error 7.5e-5, below the half-ulp 2.4e-4 of the F16 the result is rounded to),
+// and n added straight into the exponent field (LEA). 3 FADD2 + 3 FFMA2 + 2 FMNMX + 2 LEA per pair, all off the MUFU pipe.
+__device__ __forceinline__ uint64_t ex2_poly2(uint64_t x) {
+    float a, b;
+    unpack2(x, a, b);
+    const uint64_t xc = pack2(fmaxf(a, -126.f), fmaxf(b, -126.f));   // keeps the exponent arithmetic in range (masked -inf -> 2^-126 -> 0 in F16)
+    const uint64_t t = add2_rm(xc, pack2(12582912.f, 12582912.f));   // low mantissa bits = floor(x)
+    const uint64_t fl = add2(t, pack2(-12582912.f, -12582912.f));
+    float l0, l1;
+    unpack2(fl, l0, l1);
+    const uint64_t f = add2(xc, pack2(-l0, -l1));
+    uint64_t p = fma2(pack2(0.07802393f, 0.07802393f), f, pack2(0.22606699f, 0.22606699f));
+    p = fma2(p, f, pack2(0.69583416f, 0.69583416f));
+    p = fma2(p, f, pack2(0.99992508f, 0.99992508f));
+    float p0, p1, t0, t1;
+    unpack2(p, p0, p1);
+    unpack2(t, t0, t1);
+    return pack2(__uint_as_float((__float_as_uint(t0) << 23) + __float_as_uint(p0)),
+                 __uint_as_float((__float_as_uint(t1) << 23) + __float_as_uint(p1)));
 }
 
 __device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t (&r)[32]) {
@@ -78,6 +129,8 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, ui
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// NPOLY = how many of every 8 element pairs take ex2_poly2 (FMA pipe) instead of MUFU.EX2 (16 / clk / SM, the binding unit)
+template <int NPOLY>
 __global__ void __launch_bounds__(THREADS, 2)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tm, __half* __restrict__ out, int T, int D) {
     extern __shared__ uint8_t smem_raw[];
@@ -206,7 +259,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm, __half* __restrict__
 #pragma unroll
                 for (int c4 = 0; c4 < 4; ++c4)
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) m4[c4] = fmaxf(m4[c4], __uint_as_float(s[c4][i]));   // 4 independent chains
+                    for (int i = 0; i < 32; i += 2)   // FMNMX3: two elements per issue slot, 4 independent chains
+                        m4[c4] = max3(m4[c4], __uint_as_float(s[c4][i]), __uint_as_float(s[c4][i + 1]));
                 mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
             }
             mx *= LOG2E;   // log2 domain; p = ex2(s * log2e - m) is one FFMA + one MUFU per element
@@ -224,19 +278,34 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm, __half* __restrict__
             const bool any_need = __any_sync(0xffffffffu, need);
             // ---- probabilities
             uint32_t pk[4][16];
-            float rs4[4] = {0.f, 0.f, 0.f, 0.f};
+            uint64_t rs2[4] = {0ull, 0ull, 0ull, 0ull};   // packed (even, odd) partial row sums
+            const uint64_t l2e2 = pack2(LOG2E, LOG2E), nm2 = pack2(-m_used, -m_used);
 #pragma unroll
             for (int c4 = 0; c4 < 4; ++c4)
 #pragma unroll
                 for (int i = 0; i < 32; i += 2) {
-                    const float x0 = fmaf(__uint_as_float(s[c4][i]), LOG2E, -m_used);
-                    const float x1 = fmaf(__uint_as_float(s[c4][i + 1]), LOG2E, -m_used);
-                    const float p0 = ex2(x0);
-                    const float p1 = ex2(x1);
-                    rs4[c4] += p0 + p1;
+                    const uint64_t x = fma2(pack2(__uint_as_float(s[c4][i]), __uint_as_float(s[c4][i + 1])), l2e2, nm2);
+                    uint64_t p;
+                    if (((i >> 1) & 7) < NPOLY) {
+                        p = ex2_poly2(x);
+                    } else {
+                        float x0, x1;
+                        unpack2(x, x0, x1);
+                        p = pack2(ex2(x0), ex2(x1));
+                    }
+                    rs2[c4] = add2(rs2[c4], p);
+                    float p0, p1;
+                    unpack2(p, p0, p1);
                     __half2 hh = __floats2half2_rn(p0, p1);
                     pk[c4][i >> 1] = *reinterpret_cast<uint32_t*>(&hh);
                 }
+            float rs4[4];
+#pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4) {
+                float a, b;
+                unpack2(rs2[c4], a, b);
+                rs4[c4] = a + b;
+            }
             l_sum += (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]);
             // ---- P and V buffers free, O_{j-1} accumulated
             if (j > 0) {
@@ -330,14 +399,30 @@ cudaError_t attention_f16_tcgen05(const __half* qkv, __half* out, int B, int T, 
     if (enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<__half*>(qkv), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
         return cudaErrorInvalidValue;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-        if (e != cudaSuccess) return e;
-        configured = true;
+    static int npoly = -1;
+    if (npoly < 0) {
+        const char* e = getenv("Q2W_ATT_POLY");   // experiment knob: pairs of every 8 on the FMA-pipe exponential (0 = all MUFU)
+        int np = e ? atoi(e) : ATT_POLY_DEFAULT;
+        if (np < 0 || np > 4) np = ATT_POLY_DEFAULT;
+        cudaError_t err = cudaSuccess;
+        switch (np) {
+            case 0: err = cudaFuncSetAttribute(attention_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES); break;
+            case 1: err = cudaFuncSetAttribute(attention_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES); break;
+            case 2: err = cudaFuncSetAttribute(attention_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES); break;
+            case 3: err = cudaFuncSetAttribute(attention_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES); break;
+            default: err = cudaFuncSetAttribute(attention_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES); break;
+        }
+        if (err != cudaSuccess) return err;
+        npoly = np;
     }
     dim3 grid((T + BQ - 1) / BQ, H, B);
-    return launch_pdl(attention_tc_kernel, grid, dim3(THREADS), SMEM_BYTES, st, tm, out, T, D);
+    switch (npoly) {
+        case 0: return launch_pdl(attention_tc_kernel<0>, grid, dim3(THREADS), SMEM_BYTES, st, tm, out, T, D);
+        case 1: return launch_pdl(attention_tc_kernel<1>, grid, dim3(THREADS), SMEM_BYTES, st, tm, out, T, D);
+        case 2: return launch_pdl(attention_tc_kernel<2>, grid, dim3(THREADS), SMEM_BYTES, st, tm, out, T, D);
+        case 3: return launch_pdl(attention_tc_kernel<3>, grid, dim3(THREADS), SMEM_BYTES, st, tm, out, T, D);
+        default: return launch_pdl(attention_tc_kernel<4>, grid, dim3(THREADS), SMEM_BYTES, st, tm, out, T, D);
+    }
 }
 
 }  // namespace q2w
