@@ -6,23 +6,32 @@
 // Softmax follows ggml_soft_max (ggml/src/ggml.c:13854-13940): scale 1, no mask, row max subtracted, normalised by the
 // row sum; it is evaluated online in FP32, probabilities are rounded to F16 for the PV product, FP32 accumulation.
 //
-// One CTA = 128 query rows of one (window, head); 256 threads; two CTAs are resident per SM (256 TMEM columns each) so one
-// CTA's softmax (MUFU-bound) overlaps the other's MMAs.
-//   warp 0      TMA producer: Q once, then K_j / V_j tiles (128 x 64 f16, SWIZZLE_128B) through a 3-D tensor map over
-//               qkv[B][T][3D] -- rows past T are out of bounds for the map and arrive as zeros, never as the next window
-//   warp 1      MMA issuer:  S = Q K_j^T   tcgen05.mma kind::f16  M128 N128 K16 x4   (A, B K-major)          -> TMEM cols [0,128)
-//                            O += P_j V_j  tcgen05.mma kind::f16  M128 N64  K16 x8   (A = P read from TMEM cols [192,256),
+// Persistent kernel, two CTAs per SM (256 TMEM columns each), 256 threads per CTA. A work item = 128 query rows of one (window, head);
+// CTA c walks items c, c + gridDim.x, ...; the KV tile sequence is continuous across items, so nothing drains at an item boundary.
+//   warp 0      TMA producer: Q (two buffers, the next item's Q half an item ahead), K_g / V_g tiles (128 x 64 f16, SWIZZLE_128B, two
+//               stages each) through a 3-D tensor map over qkv[B][T][3D] -- rows past T are out of bounds for the map and arrive as
+//               zeros, never as the next window
+//   warp 1      MMA issuer:  S = Q K_g^T   tcgen05.mma kind::f16  M128 N128 K16 x4   (A, B K-major)          -> TMEM cols [0,128)
+//                            O += P_g V_g  tcgen05.mma kind::f16  M128 N64  K16 x8   (A = P read from TMEM cols [192,256),
 //                                                                                      B = V MN-major as loaded) -> TMEM cols [128,192)
+//               QK_{g+1} is issued before PV_g (also across items), so S_{g+1} is ready when softmax_g ends
 //   warps 4-7   softmax, one thread per query row: tcgen05.ld the S row (single pass, 128 registers), mask the ragged last
-//               tile, running max / sum in the log2 domain, ex2, pack to F16, tcgen05.st the P row back into TMEM.
-//               O stays in TMEM for the whole KV loop; it is rescaled (tcgen05.ld -> mul -> tcgen05.st) only when the
-//               running max grew by more than 2^8 since the last rescale -- the stale max is exact algebra, it only bounds
-//               the magnitude of P (<= 256 in F16), and the final division by the row sum uses the same reference point.
+//               tile, running max / sum in the log2 domain (FMNMX3, FFMA2, FADD2: two elements per issue slot), ex2, pack to F16,
+//               tcgen05.st the P row back into TMEM. O stays in TMEM for the whole KV loop; it is rescaled (tcgen05.ld -> mul ->
+//               tcgen05.st) only when the running max grew by more than 2^8 since the last rescale -- the stale max is exact algebra,
+//               it only bounds the magnitude of P (<= 256 in F16), and the final division by the row sum uses the same reference point.
+//               Item epilogue (O / l -> F16) is deferred into the next item's first tile, staged 128B-swizzled in the finished item's
+//               own Q buffer and written by ONE TMA store (rows >= T clipped by the TMA unit).
 // Registers are rebalanced with setmaxnreg (producer/MMA warpgroup 56, softmax warpgroup 200).
+// Measured (tools/ubench/xu_pipe.cu, tools/att_clk.py, make EXTRA_NVFLAGS=-DQ2W_ATT_TIMELINE): MUFU.EX2 issues at 8 clk per warp per
+// scheduler and the whole softmax instruction mix fits under it (64.6 clk per 8 elements with two warps per scheduler); the steady
+// state is ~2200 clk per tile per CTA against the 2048-clk MUFU floor of two co-resident CTAs; run back to back the kernel sits at the
+// 1000 W power cap (SM clock 1.75 GHz of 1.965), so removing idle cycles now buys clocks, not time.
 #include "ops.h"
 #include "launch.cuh"
 #include "ptx.cuh"
 
+#include <cstdio>
 #include <cstdlib>
 #include <mutex>
 
@@ -33,13 +42,13 @@ namespace {
 constexpr int HD = 64, BQ = 128, BKV = 128;
 constexpr int THREADS = 256;
 constexpr int TILE_BYTES = 128 * 128;           // 128 rows x 64 f16 = 16 KB
-constexpr int SMEM_DATA = 3 * TILE_BYTES;       // Q, K, V = 48 KB (P never touches shared memory)
-constexpr int SMEM_BYTES = SMEM_DATA + 1024 /*align*/ + 128 /*barriers*/;
+constexpr int SMEM_DATA = 6 * TILE_BYTES;       // Q x2, K x2, V x2 = 96 KB per CTA, two CTAs per SM (P never touches shared memory;
+                                                // the finished item's Q buffer doubles as the staging tile of its output store)
+constexpr int SMEM_BYTES = SMEM_DATA + 1024 /*align*/ + 256 /*barriers*/;
 constexpr int TMEM_COLS = 256;
 constexpr int S_COL = 0, O_COL = 128, P_COL = 192;   // S f32 [0,128) | O f32 [128,192) | P f16x2 [192,256)
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float RESCALE_THRESHOLD = 8.0f;       // log2 units
-constexpr int ATT_POLY_DEFAULT = 0;
 
 // MN-major operand tile written by TMA with SWIZZLE_128B: each K row is 128 B (64 f16 along N), 8-row groups 1024 B apart
 __device__ __forceinline__ uint64_t make_sw128_mnmajor_desc(uint32_t smem_addr) {
@@ -85,28 +94,6 @@ __device__ __forceinline__ float max3(float a, float b, float c) {
     asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
     return d;
 }
-// 2^x for a pair of log2-domain scores WITHOUT the MUFU: x = n + f (n = floor via the 1.5*2^23 magic add rounded down, f in [0,1)),
-// 2^f by a degree-3 minimax polynomial (max rel. error 7.5e-5, below the half-ulp 2.4e-4 of the F16 the result is rounded to),
-// and n added straight into the exponent field (LEA). 3 FADD2 + 3 FFMA2 + 2 FMNMX + 2 LEA per pair, all off the MUFU pipe.
-__device__ __forceinline__ uint64_t ex2_poly2(uint64_t x) {
-    float a, b;
-    unpack2(x, a, b);
-    const uint64_t xc = pack2(fmaxf(a, -126.f), fmaxf(b, -126.f));   // keeps the exponent arithmetic in range (masked -inf -> 2^-126 -> 0 in F16)
-    const uint64_t t = add2_rm(xc, pack2(12582912.f, 12582912.f));   // low mantissa bits = floor(x)
-    const uint64_t fl = add2(t, pack2(-12582912.f, -12582912.f));
-    float l0, l1;
-    unpack2(fl, l0, l1);
-    const uint64_t f = add2(xc, pack2(-l0, -l1));
-    uint64_t p = fma2(pack2(0.07802393f, 0.07802393f), f, pack2(0.22606699f, 0.22606699f));
-    p = fma2(p, f, pack2(0.69583416f, 0.69583416f));
-    p = fma2(p, f, pack2(0.99992508f, 0.99992508f));
-    float p0, p1, t0, t1;
-    unpack2(p, p0, p1);
-    unpack2(t, t0, t1);
-    return pack2(__uint_as_float((__float_as_uint(t0) << 23) + __float_as_uint(p0)),
-                 __uint_as_float((__float_as_uint(t1) << 23) + __float_as_uint(p1)));
-}
-
 __device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t (&r)[32]) {
     asm volatile(
         "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
@@ -128,37 +115,60 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, ui
         : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
-// NPOLY = how many of every 8 element pairs take ex2_poly2 (FMA pipe) instead of MUFU.EX2 (16 / clk / SM, the binding unit)
-template <int NPOLY>
+// Persistent: grid = 2 CTAs per SM, each CTA walks work items (window, head, 128-query tile) with stride gridDim.x. The KV tile
+// sequence is continuous across items (global tile index g): the producer prefetches the next item's Q (two Q buffers) and its
+// first K/V tiles while the current item's last tiles are still in the softmax, and the MMA warp issues S = Q' K_0'^T of the next
+// item under the current item's last exp phase -- so TMEM allocation, barrier setup, descriptor fetch and the first TMA round trip
+// (a third of a one-item CTA's lifetime, measured) are paid once per CTA instead of once per item.
 __global__ void __launch_bounds__(THREADS, 2)
-attention_tc_kernel(const __grid_constant__ CUtensorMap tm, __half* __restrict__ out, int T, int D) {
+attention_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUtensorMap tm_out, int T, int D, int n_qt, int H, int n_items) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* sQ = smem;
-    uint8_t* sK = smem + TILE_BYTES;
-    uint8_t* sV = smem + 2 * TILE_BYTES;
+    uint8_t* sQ = smem;                         // [2]
+    uint8_t* sK = smem + 2 * TILE_BYTES;        // [2]  (a single K / V buffer exposes the TMA round trip every tile: measured ~600 clk
+    uint8_t* sV = smem + 4 * TILE_BYTES;        // [2]   of s_full wait per 3000-clk tile, and PV_g queued behind the late QK_{g+1})
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SMEM_DATA);
-    uint64_t* q_full = bars + 0;
-    uint64_t* k_full = bars + 1;
-    uint64_t* k_empty = bars + 2;
-    uint64_t* v_full = bars + 3;
-    uint64_t* pv_done = bars + 4;   // PV_j complete: V and P buffers free, O_j accumulated
-    uint64_t* s_full = bars + 5;
-    uint64_t* s_empty = bars + 6;   // softmax has pulled S_j into registers
-    uint64_t* p_full = bars + 7;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+    uint64_t* q_full = bars + 0;    // [2]
+    uint64_t* q_empty = bars + 2;   // [2]  last QK of the item that used this Q buffer has completed
+    uint64_t* k_full = bars + 4;    // [2]
+    uint64_t* k_empty = bars + 6;   // [2]  QK_g complete
+    uint64_t* v_full = bars + 8;    // [2]
+    uint64_t* v_empty = bars + 10;  // [2]  PV_g complete
+    uint64_t* pv_done = bars + 12;  // PV_g complete: P buffer free, O accumulated
+    uint64_t* s_full = bars + 13;
+    uint64_t* s_empty = bars + 14;  // softmax has pulled S_g into registers
+    uint64_t* p_full = bars + 15;
+    uint64_t* q_free = bars + 16;   // [2]  the output store staged in this Q buffer has been read out
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int q0 = blockIdx.x * BQ, h = blockIdx.y, b = blockIdx.z;
     const int n_kv = (T + BKV - 1) / BKV;
+    const int first = blockIdx.x, step = gridDim.x;
+#ifdef Q2W_ATT_TIMELINE   // diagnostic build (make EXTRA_NVFLAGS=-DQ2W_ATT_TIMELINE): per-tile clock stamps of one softmax thread, printed at exit
+    __shared__ long long tl[40][6];
+    __shared__ long long tlm[40][5];
+    const bool tlm_on = blockIdx.x == 5 && warp == 1 && lane == 0;
+    const long long t_start = clock64();
+    const bool tl_on = blockIdx.x == 5 && warp == 4 && lane == 0;
+#define TL(e) if (tl_on && g < 40) tl[g][e] = clock64() - t_start
+#else
+#define TL(e)
+#endif
+    const int my_items = first < n_items ? (n_items - first + step - 1) / step : 0;
+    const int n_tiles = my_items * n_kv;   // this CTA's whole KV tile sequence
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tm);
-        mbar_init(q_full, 1);
-        mbar_init(k_full, 1);
-        mbar_init(k_empty, 1);
-        mbar_init(v_full, 1);
+        tma_prefetch_desc(&tm_out);
+        for (int i = 0; i < 2; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); mbar_init(&q_free[i], 1); }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&k_full[i], 1);
+            mbar_init(&k_empty[i], 1);
+            mbar_init(&v_full[i], 1);
+            mbar_init(&v_empty[i], 1);
+        }
         mbar_init(pv_done, 1);
         mbar_init(s_full, 1);
         mbar_init(s_empty, 128);
@@ -176,47 +186,92 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm, __half* __restrict__
     pdl_wait();                  // the QKV GEMM's output is visible from here on; the prologue above overlapped its tail
     pdl_launch_dependents();
 
+    // item -> (query tile, head, window); query tiles of one (window, head) are adjacent items so that co-running CTAs share K/V in L2
+    auto item_coords = [&](int it, int& q0, int& h, int& b) {
+        const int item = first + it * step;
+        const int qt = item % n_qt;
+        const int r = item / n_qt;
+        h = r % H;
+        b = r / H;
+        q0 = qt * BQ;
+    };
+
     if (warp < 4) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
         if (warp == 0 && lane == 0) {
             // ------------------------------------------------------------ TMA producer
-            mbar_expect_tx(q_full, TILE_BYTES);
-            tma_load_3d(sQ, &tm, q_full, h * HD, q0, b);
-            for (int j = 0; j < n_kv; ++j) {
-                if (j > 0) mbar_wait(k_empty, (j - 1) & 1);
-                mbar_expect_tx(k_full, TILE_BYTES);
-                tma_load_3d(sK, &tm, k_full, D + h * HD, j * BKV, b);
-                if (j > 0) mbar_wait(pv_done, (j - 1) & 1);
-                mbar_expect_tx(v_full, TILE_BYTES);
-                tma_load_3d(sV, &tm, v_full, 2 * D + h * HD, j * BKV, b);
+            auto load_q = [&](int it) {   // Q of item `it` into buffer it & 1 (free once the last QK of item it - 2 has completed)
+                int q0, h, b;
+                item_coords(it, q0, h, b);
+                const int qb = it & 1;
+                if (it >= 2) {
+                    mbar_wait(&q_empty[qb], ((it >> 1) - 1) & 1);   // QKs of item it - 2 done with it
+                    mbar_wait(&q_free[qb], ((it >> 1) - 1) & 1);    // ... and its output tile, staged there, stored
+                }
+                mbar_expect_tx(&q_full[qb], TILE_BYTES);
+                tma_load_3d(sQ + qb * TILE_BYTES, &tm, &q_full[qb], h * HD, q0, b);
+            };
+            int g = 0;
+            if (my_items > 0) load_q(0);
+            if (my_items > 1) load_q(1);
+            for (int it = 0; it < my_items; ++it) {
+                int q0, h, b;
+                item_coords(it, q0, h, b);
+                for (int j = 0; j < n_kv; ++j, ++g) {
+                    const int st = g & 1;
+                    if (g >= 2) mbar_wait(&k_empty[st], ((g >> 1) - 1) & 1);
+                    mbar_expect_tx(&k_full[st], TILE_BYTES);
+                    tma_load_3d(sK + st * TILE_BYTES, &tm, &k_full[st], D + h * HD, j * BKV, b);
+                    if (g >= 2) mbar_wait(&v_empty[st], ((g >> 1) - 1) & 1);
+                    mbar_expect_tx(&v_full[st], TILE_BYTES);
+                    tma_load_3d(sV + st * TILE_BYTES, &tm, &v_full[st], 2 * D + h * HD, j * BKV, b);
+                    // next item's Q goes into the buffer of item it - 1, free once that item's output (staged there during this item's
+                    // first tile) has been stored: half an item ahead of its first use
+                    if (j == n_kv / 2 && it >= 1 && it + 1 < my_items) load_q(it + 1);
+                }
             }
         } else if (warp == 1 && lane == 0) {
             // ------------------------------------------------------------ MMA issuer
             constexpr uint32_t idesc_qk = make_idesc_f16(BQ, BKV, 0, 0);
             constexpr uint32_t idesc_pv = make_idesc_f16(BQ, HD, 0, 1);     // B = V is MN-major
-            const uint64_t q_desc = make_sw128_kmajor_desc(smem_u32(sQ));
-            const uint64_t k_desc = make_sw128_kmajor_desc(smem_u32(sK));
-            const uint64_t v_desc = make_sw128_mnmajor_desc(smem_u32(sV));
-            mbar_wait(q_full, 0);
-            // software pipeline: S_{j+1} = Q K_{j+1}^T is issued BEFORE waiting for P_j, so it runs under softmax_j's exp phase
-            // (the single S buffer is free as soon as softmax_j has pulled its row into registers: s_empty).  Round-1 timeline:
-            // the in-order issue QK_j, PV_j, QK_{j+1} serialised softmax_{j+1} behind softmax_j + PV_j (4400 cycles per tile).
-            auto issue_qk = [&](int j) {
-                mbar_wait(k_full, j & 1);
-                if (j > 0) mbar_wait(s_empty, (j - 1) & 1);
+            // software pipeline: S_{g+1} = Q K_{g+1}^T is issued BEFORE waiting for P_g, so it runs under softmax_g's exp phase
+            // (the single S buffer is free as soon as softmax_g has pulled its row into registers: s_empty) -- also across items.
+            auto issue_qk = [&](int g) {
+                const int it = g / n_kv, j = g - it * n_kv;
+                const int qb = it & 1;
+                if (j == 0) mbar_wait(&q_full[qb], (it >> 1) & 1);
+                mbar_wait(&k_full[g & 1], (g >> 1) & 1);
+                if (g > 0) mbar_wait(s_empty, (g - 1) & 1);
                 tc_fence_after();
+                const uint64_t q_desc = make_sw128_kmajor_desc(smem_u32(sQ + qb * TILE_BYTES));
+                const uint64_t k_desc = make_sw128_kmajor_desc(smem_u32(sK + (g & 1) * TILE_BYTES));
 #pragma unroll
                 for (int k = 0; k < HD / 16; ++k)
                     umma_f16_ss(tmem_base + S_COL, q_desc + 2 * k, k_desc + 2 * k, idesc_qk, k != 0);
                 umma_commit(s_full);
-                umma_commit(k_empty);
+                umma_commit(&k_empty[g & 1]);
+                if (j == n_kv - 1) umma_commit(&q_empty[qb]);
             };
-            issue_qk(0);
-            for (int j = 0; j < n_kv; ++j) {
-                if (j + 1 < n_kv) issue_qk(j + 1);
-                mbar_wait(p_full, j & 1);
-                mbar_wait(v_full, j & 1);
+            if (n_tiles > 0) issue_qk(0);
+            int j = 0;
+            for (int g = 0; g < n_tiles; ++g) {
+#ifdef Q2W_ATT_TIMELINE
+                if (tlm_on && g < 40) tlm[g][0] = clock64() - t_start;
+#endif
+                if (g + 1 < n_tiles) issue_qk(g + 1);
+#ifdef Q2W_ATT_TIMELINE
+                if (tlm_on && g < 40) tlm[g][1] = clock64() - t_start;
+#endif
+                mbar_wait(p_full, g & 1);
+#ifdef Q2W_ATT_TIMELINE
+                if (tlm_on && g < 40) tlm[g][2] = clock64() - t_start;
+#endif
+                mbar_wait(&v_full[g & 1], (g >> 1) & 1);
                 tc_fence_after();
+#ifdef Q2W_ATT_TIMELINE
+                if (tlm_on && g < 40) tlm[g][3] = clock64() - t_start;
+#endif
+                const uint64_t v_desc = make_sw128_mnmajor_desc(smem_u32(sV + (g & 1) * TILE_BYTES));
 #pragma unroll
                 for (int k = 0; k < BKV / 16; ++k) {
                     // P is the A operand straight from TMEM: lane = query row, 16 f16 (one K step) = 8 packed 32-bit columns
@@ -225,6 +280,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm, __half* __restrict__
                     umma_f16_ts(tmem_base + O_COL, tmem_base + P_COL + k * 8, vb, idesc_pv, (j | k) != 0);
                 }
                 umma_commit(pv_done);
+                umma_commit(&v_empty[g & 1]);
+#ifdef Q2W_ATT_TIMELINE
+                if (tlm_on && g < 40) tlm[g][4] = clock64() - t_start;
+#endif
+                if (++j == n_kv) j = 0;
             }
         }
     } else {
@@ -233,132 +293,175 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm, __half* __restrict__
         const int qd = warp & 3;
         const int row = qd * 32 + lane;
         const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(qd * 32) << 16);
-        float m_used = -INFINITY;   // reference point of P and O, log2 domain
-        float l_sum = 0.f;
-        for (int j = 0; j < n_kv; ++j) {
-            mbar_wait(s_full, j & 1);
-            tc_fence_after();
-            uint32_t s[4][32];
+        // item epilogue: O / l -> f16 -> the item's own (now idle) Q buffer, 128-byte swizzled -> ONE TMA store of the 128 x 64 tile.
+        // Per-thread global stores of a 128-byte row cost 32 L1 line transactions per instruction (1024 per item, measured ~1500 clk);
+        // the TMA store writes whole lines and clips rows >= T itself. The producer reloads the buffer only after q_free.
+        const bool epi_leader = warp == 4 && lane == 0;
+        auto item_epilogue = [&](float inv, int q0, int h, int b, int qb) {
+            uint8_t* stage = sQ + qb * TILE_BYTES;
 #pragma unroll
-            for (int c4 = 0; c4 < 4; ++c4) tmem_ld_32x32b_x32(t_lane + S_COL + c4 * 32, s[c4]);
-            tmem_ld_wait();
-            tc_fence_before();
-            mbar_arrive(s_empty);
-            // ---- row max (log2 domain), ragged last tile masked
-            const int valid = T - j * BKV;   // >= 1
-            float mx = -INFINITY;
-            if (valid < BKV) {               // warp-uniform
+            for (int hh = 0; hh < 2; ++hh) {
+                uint32_t o[32];
+                tmem_ld_32x32b_x32(t_lane + O_COL + hh * 32, o);
+                tmem_ld_wait();
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {                  // SWIZZLE_128B: 16-byte chunk index ^= row & 7
+                    uint32_t w[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        __half2 v = __floats2half2_rn(__uint_as_float(o[8 * c + 2 * i]) * inv, __uint_as_float(o[8 * c + 2 * i + 1]) * inv);
+                        w[i] = *reinterpret_cast<uint32_t*>(&v);
+                    }
+                    *reinterpret_cast<uint4*>(stage + row * 128 + (((hh * 4 + c) ^ (row & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+            }
+            fence_proxy_async_smem();
+            named_bar_sync(1, 128);
+            if (epi_leader) {
+                tma_store_3d(&tm_out, stage, h * HD, q0, b);
+                bulk_commit_group();
+            }
+        };
+        int g = 0;
+        float prev_inv = 0.f;
+        int prev_q0 = 0, prev_h = 0, prev_b = 0;
+        const int release_tile = n_kv > 1 ? 1 : 0;   // the tile after which the leader hands the staged Q buffer back to the producer
+        for (int it = 0; it < my_items; ++it) {
+            int q0, h, b;
+            item_coords(it, q0, h, b);
+            float m_used = -INFINITY;   // reference point of P and O, log2 domain
+            float l_sum = 0.f;
+            for (int j = 0; j < n_kv; ++j, ++g) {
+                TL(0);
+                mbar_wait(s_full, g & 1);
+                tc_fence_after();
+                TL(1);
+                uint32_t s[4][32];
+#pragma unroll
+                for (int c4 = 0; c4 < 4; ++c4) tmem_ld_32x32b_x32(t_lane + S_COL + c4 * 32, s[c4]);
+                tmem_ld_wait();
+                TL(2);
+                tc_fence_before();
+                mbar_arrive(s_empty);
+                // ---- row max (log2 domain), ragged last tile masked
+                const int valid = T - j * BKV;   // >= 1
+                float mx = -INFINITY;
+                if (valid < BKV) {               // warp-uniform
+#pragma unroll
+                    for (int c4 = 0; c4 < 4; ++c4)
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (c4 * 32 + i >= valid) s[c4][i] = __float_as_uint(-INFINITY);
+                }
+                {
+                    float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+                    for (int c4 = 0; c4 < 4; ++c4)
+#pragma unroll
+                        for (int i = 0; i < 32; i += 2)   // FMNMX3: two elements per issue slot, 4 independent chains
+                            m4[c4] = max3(m4[c4], __uint_as_float(s[c4][i]), __uint_as_float(s[c4][i + 1]));
+                    mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+                }
+                mx *= LOG2E;   // log2 domain; p = ex2(s * log2e - m) is one FFMA + one MUFU per element
+                // ---- lazy rescale decision (warp-uniform because tcgen05.ld/st are warp-collective)
+                float factor = 1.0f;
+                bool need = false;
+                if (j == 0) {
+                    m_used = mx;
+                } else if (mx - m_used > RESCALE_THRESHOLD) {
+                    need = true;
+                    factor = ex2(m_used - mx);
+                    m_used = mx;
+                    l_sum *= factor;
+                }
+                const bool any_need = __any_sync(0xffffffffu, need);
+                // ---- probabilities (packed FFMA2 / FADD2: one issue slot per two elements)
+                uint32_t pk[4][16];
+                uint64_t rs2[4] = {0ull, 0ull, 0ull, 0ull};   // packed (even, odd) partial row sums
+                const uint64_t l2e2 = pack2(LOG2E, LOG2E), nm2 = pack2(-m_used, -m_used);
 #pragma unroll
                 for (int c4 = 0; c4 < 4; ++c4)
 #pragma unroll
-                    for (int i = 0; i < 32; ++i)
-                        if (c4 * 32 + i >= valid) s[c4][i] = __float_as_uint(-INFINITY);
-            }
-            {
-                float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll
-                for (int c4 = 0; c4 < 4; ++c4)
-#pragma unroll
-                    for (int i = 0; i < 32; i += 2)   // FMNMX3: two elements per issue slot, 4 independent chains
-                        m4[c4] = max3(m4[c4], __uint_as_float(s[c4][i]), __uint_as_float(s[c4][i + 1]));
-                mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
-            }
-            mx *= LOG2E;   // log2 domain; p = ex2(s * log2e - m) is one FFMA + one MUFU per element
-            // ---- lazy rescale decision (warp-uniform because tcgen05.ld/st are warp-collective)
-            float factor = 1.0f;
-            bool need = false;
-            if (j == 0) {
-                m_used = mx;
-            } else if (mx - m_used > RESCALE_THRESHOLD) {
-                need = true;
-                factor = ex2(m_used - mx);
-                m_used = mx;
-                l_sum *= factor;
-            }
-            const bool any_need = __any_sync(0xffffffffu, need);
-            // ---- probabilities
-            uint32_t pk[4][16];
-            uint64_t rs2[4] = {0ull, 0ull, 0ull, 0ull};   // packed (even, odd) partial row sums
-            const uint64_t l2e2 = pack2(LOG2E, LOG2E), nm2 = pack2(-m_used, -m_used);
-#pragma unroll
-            for (int c4 = 0; c4 < 4; ++c4)
-#pragma unroll
-                for (int i = 0; i < 32; i += 2) {
-                    const uint64_t x = fma2(pack2(__uint_as_float(s[c4][i]), __uint_as_float(s[c4][i + 1])), l2e2, nm2);
-                    uint64_t p;
-                    if (((i >> 1) & 7) < NPOLY) {
-                        p = ex2_poly2(x);
-                    } else {
+                    for (int i = 0; i < 32; i += 2) {
+                        const uint64_t x = fma2(pack2(__uint_as_float(s[c4][i]), __uint_as_float(s[c4][i + 1])), l2e2, nm2);
                         float x0, x1;
                         unpack2(x, x0, x1);
-                        p = pack2(ex2(x0), ex2(x1));
+                        const float p0 = ex2(x0), p1 = ex2(x1);
+                        rs2[c4] = add2(rs2[c4], pack2(p0, p1));
+                        __half2 hh = __floats2half2_rn(p0, p1);
+                        pk[c4][i >> 1] = *reinterpret_cast<uint32_t*>(&hh);
                     }
-                    rs2[c4] = add2(rs2[c4], p);
-                    float p0, p1;
-                    unpack2(p, p0, p1);
-                    __half2 hh = __floats2half2_rn(p0, p1);
-                    pk[c4][i >> 1] = *reinterpret_cast<uint32_t*>(&hh);
+                float rs4[4];
+#pragma unroll
+                for (int c4 = 0; c4 < 4; ++c4) {
+                    float a, bb;
+                    unpack2(rs2[c4], a, bb);
+                    rs4[c4] = a + bb;
                 }
-            float rs4[4];
+                l_sum += (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]);
+                // ---- P buffer free, O_{g-1} accumulated
+                if (g > 0) {
+                    mbar_wait(pv_done, (g - 1) & 1);
+                    tc_fence_after();
+                    if (j == 0) {
+                        // the previous item's O is complete and this item's first PV (accumulate = 0 into the same columns) is only
+                        // issued after the p_full arrival below: its epilogue runs here, a whole exp phase after its last PV was
+                        // issued, instead of waiting for that PV at the item boundary (measured 1300-1700 clk of idle MUFU)
+                        item_epilogue(prev_inv, prev_q0, prev_h, prev_b, (it - 1) & 1);
+                        tc_fence_before();
+                    } else if (any_need) {
+                        uint32_t o[32];
 #pragma unroll
-            for (int c4 = 0; c4 < 4; ++c4) {
-                float a, b;
-                unpack2(rs2[c4], a, b);
-                rs4[c4] = a + b;
-            }
-            l_sum += (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]);
-            // ---- P and V buffers free, O_{j-1} accumulated
-            if (j > 0) {
-                mbar_wait(pv_done, (j - 1) & 1);
-                tc_fence_after();
-                if (any_need) {
-                    uint32_t o[32];
+                        for (int hh = 0; hh < 2; ++hh) {
+                            tmem_ld_32x32b_x32(t_lane + O_COL + hh * 32, o);
+                            tmem_ld_wait();
 #pragma unroll
-                    for (int hh = 0; hh < 2; ++hh) {
-                        tmem_ld_32x32b_x32(t_lane + O_COL + hh * 32, o);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * factor);
-                        tmem_st_32x32b_x32(t_lane + O_COL + hh * 32, o);
+                            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * factor);
+                            tmem_st_32x32b_x32(t_lane + O_COL + hh * 32, o);
+                        }
+                        tmem_st_wait();
                     }
-                    tmem_st_wait();
                 }
+                // ---- P row -> TMEM columns [192,256) (two f16 per 32-bit column): no shared memory, no proxy fence
+                tmem_st_32x32b_x32(t_lane + P_COL, *reinterpret_cast<uint32_t (*)[32]>(&pk[0][0]));
+                tmem_st_32x32b_x32(t_lane + P_COL + 32, *reinterpret_cast<uint32_t (*)[32]>(&pk[2][0]));
+                TL(3);
+                tmem_st_wait();
+                TL(4);
+                tc_fence_before();
+                mbar_arrive(p_full);
+                TL(5);
+                if (it > 0 && j == release_tile && epi_leader) {
+                    bulk_wait_group_read<0>();                 // issued a tile ago: normally long complete
+                    mbar_arrive(&q_free[(it - 1) & 1]);
+                }
+                __syncwarp();
             }
-            // ---- P row -> TMEM columns [192,256) (two f16 per 32-bit column): no shared memory, no proxy fence
-            tmem_st_32x32b_x32(t_lane + P_COL, *reinterpret_cast<uint32_t (*)[32]>(&pk[0][0]));
-            tmem_st_32x32b_x32(t_lane + P_COL + 32, *reinterpret_cast<uint32_t (*)[32]>(&pk[2][0]));
-            tmem_st_wait();
+            prev_inv = 1.0f / l_sum;
+            prev_q0 = q0;
+            prev_h = h;
+            prev_b = b;
+        }
+        if (my_items > 0) {   // the last item's epilogue
+            mbar_wait(pv_done, (g - 1) & 1);
+            tc_fence_after();
+            item_epilogue(prev_inv, prev_q0, prev_h, prev_b, (my_items - 1) & 1);
             tc_fence_before();
-            mbar_arrive(p_full);
         }
-        // ---- epilogue: O / l -> f16 -> global (each thread owns one 128-byte row segment)
-        mbar_wait(pv_done, (n_kv - 1) & 1);
-        tc_fence_after();
-        const float inv = 1.0f / l_sum;
-        const int qrow = q0 + row;
-        __half* orow = out + (static_cast<size_t>(b) * T + qrow) * D + h * HD;
-#pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-            uint32_t o[32];
-            tmem_ld_32x32b_x32(t_lane + O_COL + hh * 32, o);
-            tmem_ld_wait();
-            if (qrow < T) {
-#pragma unroll
-                for (int i = 0; i < 32; i += 8) {
-                    uint4 v;
-                    __half2 a0 = __floats2half2_rn(__uint_as_float(o[i + 0]) * inv, __uint_as_float(o[i + 1]) * inv);
-                    __half2 a1 = __floats2half2_rn(__uint_as_float(o[i + 2]) * inv, __uint_as_float(o[i + 3]) * inv);
-                    __half2 a2 = __floats2half2_rn(__uint_as_float(o[i + 4]) * inv, __uint_as_float(o[i + 5]) * inv);
-                    __half2 a3 = __floats2half2_rn(__uint_as_float(o[i + 6]) * inv, __uint_as_float(o[i + 7]) * inv);
-                    v.x = *reinterpret_cast<uint32_t*>(&a0); v.y = *reinterpret_cast<uint32_t*>(&a1);
-                    v.z = *reinterpret_cast<uint32_t*>(&a2); v.w = *reinterpret_cast<uint32_t*>(&a3);
-                    *reinterpret_cast<uint4*>(orow + hh * 32 + i) = v;
-                }
-            }
-        }
-        tc_fence_before();
+        if (epi_leader) bulk_wait_group<0>();   // shared memory must outlive the last store's reads (and be safe: its writes too)
     }
 
+#ifdef Q2W_ATT_TIMELINE
+    __syncthreads();
+    if (tl_on) printf("CTA %d: %d items, %lld cycles in total = %lld per item\n", (int)blockIdx.x, my_items, clock64() - t_start, (clock64() - t_start) / my_items);
+    if (tl_on)
+        for (int g = 8; g < 16 && g < n_tiles; ++g)
+            printf("mma g%2d: loop top %lld, qk(g+1) issued %lld, p_full %lld, v_full %lld, pv issued %lld\n", g, tlm[g][0], tlm[g][1], tlm[g][2], tlm[g][3], tlm[g][4]);
+    if (tl_on)
+        for (int g = 0; g < 40 && g < n_tiles; ++g)
+            printf("g%2d top %6lld s_full %6lld (+%4lld) ld %6lld (+%4lld) st_issued %6lld (+%5lld) st_done %6lld (+%4lld) arrive +%lld\n", g, tl[g][0], tl[g][1],
+                   tl[g][1] - tl[g][0], tl[g][2], tl[g][2] - tl[g][1], tl[g][3], tl[g][3] - tl[g][2], tl[g][4], tl[g][4] - tl[g][3], tl[g][5] - tl[g][4]);
+#endif
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
@@ -399,30 +502,30 @@ cudaError_t attention_f16_tcgen05(const __half* qkv, __half* out, int B, int T, 
     if (enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<__half*>(qkv), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
         return cudaErrorInvalidValue;
-    static int npoly = -1;
-    if (npoly < 0) {
-        const char* e = getenv("Q2W_ATT_POLY");   // experiment knob: pairs of every 8 on the FMA-pipe exponential (0 = all MUFU)
-        int np = e ? atoi(e) : ATT_POLY_DEFAULT;
-        if (np < 0 || np > 4) np = ATT_POLY_DEFAULT;
-        cudaError_t err = cudaSuccess;
-        switch (np) {
-            case 0: err = cudaFuncSetAttribute(attention_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES); break;
-            case 1: err = cudaFuncSetAttribute(attention_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES); break;
-            case 2: err = cudaFuncSetAttribute(attention_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES); break;
-            case 3: err = cudaFuncSetAttribute(attention_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES); break;
-            default: err = cudaFuncSetAttribute(attention_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES); break;
-        }
+    // out viewed as [B][T][D] f16, boxes of 128 rows x 64 columns (one head): rows >= T are clipped by the TMA unit
+    CUtensorMap tm_out;
+    {
+        cuuint64_t odims[3] = {static_cast<cuuint64_t>(D), static_cast<cuuint64_t>(T), static_cast<cuuint64_t>(B)};
+        cuuint64_t ostrides[2] = {static_cast<cuuint64_t>(D) * sizeof(__half), static_cast<cuuint64_t>(T) * D * sizeof(__half)};
+        cuuint32_t obox[3] = {HD, BQ, 1};
+        if (enc(&tm_out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, out, odims, ostrides, obox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return cudaErrorInvalidValue;
+    }
+    static int num_sms = 0;
+    if (num_sms == 0) {
+        cudaError_t err = cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
         if (err != cudaSuccess) return err;
-        npoly = np;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
     }
-    dim3 grid((T + BQ - 1) / BQ, H, B);
-    switch (npoly) {
-        case 0: return launch_pdl(attention_tc_kernel<0>, grid, dim3(THREADS), SMEM_BYTES, st, tm, out, T, D);
-        case 1: return launch_pdl(attention_tc_kernel<1>, grid, dim3(THREADS), SMEM_BYTES, st, tm, out, T, D);
-        case 2: return launch_pdl(attention_tc_kernel<2>, grid, dim3(THREADS), SMEM_BYTES, st, tm, out, T, D);
-        case 3: return launch_pdl(attention_tc_kernel<3>, grid, dim3(THREADS), SMEM_BYTES, st, tm, out, T, D);
-        default: return launch_pdl(attention_tc_kernel<4>, grid, dim3(THREADS), SMEM_BYTES, st, tm, out, T, D);
-    }
+    const int n_qt = (T + BQ - 1) / BQ;
+    const long long items = static_cast<long long>(n_qt) * H * B;
+    if (items > 0x7fffffffLL / ((T + BKV - 1) / BKV)) return cudaErrorInvalidValue;
+    const int n_items = static_cast<int>(items);
+    const int grid = n_items < 2 * num_sms ? n_items : 2 * num_sms;   // persistent: two CTAs per SM
+    return launch_pdl(attention_tc_kernel, dim3(grid), dim3(THREADS), SMEM_BYTES, st, tm, tm_out, T, D, n_qt, H, n_items);
 }
 
 }  // namespace q2w
