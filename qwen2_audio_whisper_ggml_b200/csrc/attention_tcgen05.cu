@@ -453,6 +453,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constan
 
 #ifdef Q2W_ATT_TIMELINE
     __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t smid;
+        unsigned long long gt;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        printf("cta %d sm %u items %d cycles %lld end_ns %llu\n", (int)blockIdx.x, smid, my_items, clock64() - t_start, gt);
+    }
     if (tl_on) printf("CTA %d: %d items, %lld cycles in total = %lld per item\n", (int)blockIdx.x, my_items, clock64() - t_start, (clock64() - t_start) / my_items);
     if (tl_on)
         for (int g = 8; g < 16 && g < n_tiles; ++g)
