@@ -132,7 +132,8 @@ def test_pool_layernorm(lib, B, T, D):
     assert max_abs(y.cpu().numpy(), want.cpu().numpy()) < 2e-5
 
 
-@pytest.mark.parametrize("B,T,H", [(1, 64, 2), (2, 100, 2), (1, 1500, 20), (3, 333, 4)])
+# the last four shapes give every persistent CTA several work items (1-, 2-, 3- and 12-tile KV sequences)
+@pytest.mark.parametrize("B,T,H", [(1, 64, 2), (2, 100, 2), (1, 1500, 20), (3, 333, 4), (40, 100, 20), (12, 129, 20), (16, 300, 20), (8, 1500, 20)])
 def test_attention(lib, B, T, H):
     D = 64 * H
     g = torch.Generator(device="cuda").manual_seed(B * 100 + T + H)
@@ -145,6 +146,29 @@ def test_attention(lib, B, T, H):
     q, k, v = f[:, :, 0].permute(0, 2, 1, 3), f[:, :, 1].permute(0, 2, 1, 3), f[:, :, 2].permute(0, 2, 1, 3)
     p = torch.softmax(q @ k.transpose(-1, -2), dim=-1)
     want = (p @ v).permute(0, 2, 1, 3).reshape(B * T, D)
+    got = out.float().cpu().numpy()
+    assert np.isfinite(got).all()
+    assert rel_l2(got, want.cpu().numpy()) < 2e-3, rel_l2(got, want.cpu().numpy())
+
+
+def test_attention_growing_scores_take_the_rescale_path(lib):
+    """keys whose scores grow along the sequence: the running row max rises by far more than 2^8 between KV tiles, so the lazy
+    O rescale (tcgen05.ld -> mul -> tcgen05.st) runs on most tiles, across several items per CTA"""
+    B, T, H = 6, 700, 20
+    D = 64 * H
+    g = torch.Generator(device="cuda").manual_seed(77)
+    f = torch.randn(B, T, 3, H, 64, device="cuda", generator=g)
+    f[:, :, 0] = f[:, :, 0].abs() * 0.5                                    # positive queries ...
+    ramp = torch.linspace(0.05, 3.0, T, device="cuda").view(1, T, 1, 1)
+    f[:, :, 1] = f[:, :, 1].abs() * ramp                                    # ... against keys that grow with position: scores up to ~100
+    qkv = f.reshape(B * T, 3 * D).half()
+    out = torch.full((B * T, D), float("nan"), device="cuda", dtype=torch.half)
+    ck(lib.q2w_op_attention(qkv.data_ptr(), out.data_ptr(), B, T, H, None))
+    ff = qkv.float().view(B, T, 3, H, 64)
+    q, k, v = ff[:, :, 0].permute(0, 2, 1, 3), ff[:, :, 1].permute(0, 2, 1, 3), ff[:, :, 2].permute(0, 2, 1, 3)
+    s_ = q @ k.transpose(-1, -2)
+    assert float((s_.max(-1).values - s_[..., :128].max(-1).values).median()) > 20.0   # the max really moves between tiles
+    want = (torch.softmax(s_, dim=-1) @ v).permute(0, 2, 1, 3).reshape(B * T, D)
     got = out.float().cpu().numpy()
     assert np.isfinite(got).all()
     assert rel_l2(got, want.cpu().numpy()) < 2e-3, rel_l2(got, want.cpu().numpy())
