@@ -123,7 +123,8 @@ __device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("ba
 // item under the current item's last exp phase -- so TMEM allocation, barrier setup, descriptor fetch and the first TMA round trip
 // (a third of a one-item CTA's lifetime, measured) are paid once per CTA instead of once per item.
 __global__ void __launch_bounds__(THREADS, 2)
-attention_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUtensorMap tm_out, int T, int D, int n_qt, int H, int n_items) {
+attention_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUtensorMap tm_out, int T, int D, int n_qt, int H, int n_items,
+                    int* __restrict__ sched /* [0] next item, [1] finished CTAs; zero on entry, zero again on exit */) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sQ = smem;                         // [2]
@@ -141,28 +142,26 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constan
     uint64_t* s_empty = bars + 14;  // softmax has pulled S_g into registers
     uint64_t* p_full = bars + 15;
     uint64_t* q_free = bars + 16;   // [2]  the output store staged in this Q buffer has been read out
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+    uint64_t* id_full = bars + 18;  // [2]  item_ring[it & 3] holds the id of this CTA's it-th item (or -1: no more work)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+    volatile int* item_ring = reinterpret_cast<volatile int*>(tmem_slot + 1);   // [4]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_kv = (T + BKV - 1) / BKV;
-    const int first = blockIdx.x, step = gridDim.x;
 #ifdef Q2W_ATT_TIMELINE   // diagnostic build (make EXTRA_NVFLAGS=-DQ2W_ATT_TIMELINE): per-tile clock stamps of one softmax thread, printed at exit
     __shared__ long long tl[40][6];
-    __shared__ long long tlm[40][5];
-    const bool tlm_on = blockIdx.x == 5 && warp == 1 && lane == 0;
     const long long t_start = clock64();
     const bool tl_on = blockIdx.x == 5 && warp == 4 && lane == 0;
 #define TL(e) if (tl_on && g < 40) tl[g][e] = clock64() - t_start
 #else
 #define TL(e)
 #endif
-    const int my_items = first < n_items ? (n_items - first + step - 1) / step : 0;
-    const int n_tiles = my_items * n_kv;   // this CTA's whole KV tile sequence
+    int items_done = 0;   // (softmax warps) how many items this CTA ended up processing
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tm);
         tma_prefetch_desc(&tm_out);
-        for (int i = 0; i < 2; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); mbar_init(&q_free[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); mbar_init(&q_free[i], 1); mbar_init(&id_full[i], 1); }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&k_full[i], 1);
             mbar_init(&k_empty[i], 1);
@@ -186,9 +185,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constan
     pdl_wait();                  // the QKV GEMM's output is visible from here on; the prologue above overlapped its tail
     pdl_launch_dependents();
 
+    // Work is PULLED: the producer thread takes the next item from a global counter and publishes it to the other roles through
+    // item_ring / id_full. With a static split the two CTAs of an SM drift apart (whichever wins issue priority finishes up to 35 %
+    // earlier, measured) and the loser runs its tail alone, where one softmax warp per scheduler cannot keep the MUFU fed.
     // item -> (query tile, head, window); query tiles of one (window, head) are adjacent items so that co-running CTAs share K/V in L2
-    auto item_coords = [&](int it, int& q0, int& h, int& b) {
-        const int item = first + it * step;
+    auto item_id = [&](int it) {   // id of this CTA's it-th item, -1 when there is none
+        mbar_wait(&id_full[it & 1], (it >> 1) & 1);
+        return item_ring[it & 3];
+    };
+    auto item_coords = [&](int item, int& q0, int& h, int& b) {
         const int qt = item % n_qt;
         const int r = item / n_qt;
         h = r % H;
@@ -200,23 +205,30 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constan
         asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
         if (warp == 0 && lane == 0) {
             // ------------------------------------------------------------ TMA producer
-            auto load_q = [&](int it) {   // Q of item `it` into buffer it & 1 (free once the last QK of item it - 2 has completed)
-                int q0, h, b;
-                item_coords(it, q0, h, b);
+            // take the next item, wait until the Q buffer (and id slot) of item it - 2 is really retired, publish, start the Q load
+            auto next_item = [&](int it) {
+                // every CTA's first item is its own index (no round trip before the first loads); the counter hands out the rest
+                const int id = it == 0 ? static_cast<int>(blockIdx.x) : static_cast<int>(gridDim.x) + atomicAdd(sched, 1);
                 const int qb = it & 1;
                 if (it >= 2) {
-                    mbar_wait(&q_empty[qb], ((it >> 1) - 1) & 1);   // QKs of item it - 2 done with it
+                    mbar_wait(&q_empty[qb], ((it >> 1) - 1) & 1);   // QKs of item it - 2 done with the buffer
                     mbar_wait(&q_free[qb], ((it >> 1) - 1) & 1);    // ... and its output tile, staged there, stored
                 }
+                item_ring[it & 3] = id < n_items ? id : -1;
+                mbar_arrive(&id_full[qb]);                          // release: the slot is written
+                if (id >= n_items) return -1;
+                int q0, h, b;
+                item_coords(id, q0, h, b);
                 mbar_expect_tx(&q_full[qb], TILE_BYTES);
                 tma_load_3d(sQ + qb * TILE_BYTES, &tm, &q_full[qb], h * HD, q0, b);
+                return id;
             };
             int g = 0;
-            if (my_items > 0) load_q(0);
-            if (my_items > 1) load_q(1);
-            for (int it = 0; it < my_items; ++it) {
+            int cur = next_item(0);
+            int nxt = -1;
+            for (int it = 0; cur >= 0; ++it) {
                 int q0, h, b;
-                item_coords(it, q0, h, b);
+                item_coords(cur, q0, h, b);
                 for (int j = 0; j < n_kv; ++j, ++g) {
                     const int st = g & 1;
                     if (g >= 2) mbar_wait(&k_empty[st], ((g >> 1) - 1) & 1);
@@ -225,10 +237,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constan
                     if (g >= 2) mbar_wait(&v_empty[st], ((g >> 1) - 1) & 1);
                     mbar_expect_tx(&v_full[st], TILE_BYTES);
                     tma_load_3d(sV + st * TILE_BYTES, &tm, &v_full[st], 2 * D + h * HD, j * BKV, b);
-                    // next item's Q goes into the buffer of item it - 1, free once that item's output (staged there during this item's
-                    // first tile) has been stored: half an item ahead of its first use
-                    if (j == n_kv / 2 && it >= 1 && it + 1 < my_items) load_q(it + 1);
+                    // the item after this one: its Q goes into the buffer of item it - 1, free once that item's output (staged there
+                    // during this item's first tile) has been stored -- half an item ahead of its first use
+                    // (the second item right after the first tile's loads: both Q buffers are still unused)
+                    if (j == (it == 0 ? 0 : n_kv / 2)) nxt = next_item(it + 1);
                 }
+                cur = nxt;
             }
         } else if (warp == 1 && lane == 0) {
             // ------------------------------------------------------------ MMA issuer
@@ -236,8 +250,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constan
             constexpr uint32_t idesc_pv = make_idesc_f16(BQ, HD, 0, 1);     // B = V is MN-major
             // software pipeline: S_{g+1} = Q K_{g+1}^T is issued BEFORE waiting for P_g, so it runs under softmax_g's exp phase
             // (the single S buffer is free as soon as softmax_g has pulled its row into registers: s_empty) -- also across items.
-            auto issue_qk = [&](int g) {
-                const int it = g / n_kv, j = g - it * n_kv;
+            auto issue_qk = [&](int it, int j, int g) {
                 const int qb = it & 1;
                 if (j == 0) mbar_wait(&q_full[qb], (it >> 1) & 1);
                 mbar_wait(&k_full[g & 1], (g >> 1) & 1);
@@ -252,39 +265,31 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constan
                 umma_commit(&k_empty[g & 1]);
                 if (j == n_kv - 1) umma_commit(&q_empty[qb]);
             };
-            if (n_tiles > 0) issue_qk(0);
-            int j = 0;
-            for (int g = 0; g < n_tiles; ++g) {
-#ifdef Q2W_ATT_TIMELINE
-                if (tlm_on && g < 40) tlm[g][0] = clock64() - t_start;
-#endif
-                if (g + 1 < n_tiles) issue_qk(g + 1);
-#ifdef Q2W_ATT_TIMELINE
-                if (tlm_on && g < 40) tlm[g][1] = clock64() - t_start;
-#endif
-                mbar_wait(p_full, g & 1);
-#ifdef Q2W_ATT_TIMELINE
-                if (tlm_on && g < 40) tlm[g][2] = clock64() - t_start;
-#endif
-                mbar_wait(&v_full[g & 1], (g >> 1) & 1);
-                tc_fence_after();
-#ifdef Q2W_ATT_TIMELINE
-                if (tlm_on && g < 40) tlm[g][3] = clock64() - t_start;
-#endif
-                const uint64_t v_desc = make_sw128_mnmajor_desc(smem_u32(sV + (g & 1) * TILE_BYTES));
+            int g = 0;
+            bool more = item_id(0) >= 0;
+            if (more) issue_qk(0, 0, 0);
+            for (int it = 0; more; ++it) {
+                for (int j = 0; j < n_kv; ++j, ++g) {
+                    if (j + 1 < n_kv) {
+                        issue_qk(it, j + 1, g + 1);
+                    } else {
+                        more = item_id(it + 1) >= 0;
+                        if (more) issue_qk(it + 1, 0, g + 1);
+                    }
+                    mbar_wait(p_full, g & 1);
+                    mbar_wait(&v_full[g & 1], (g >> 1) & 1);
+                    tc_fence_after();
+                    const uint64_t v_desc = make_sw128_mnmajor_desc(smem_u32(sV + (g & 1) * TILE_BYTES));
 #pragma unroll
-                for (int k = 0; k < BKV / 16; ++k) {
-                    // P is the A operand straight from TMEM: lane = query row, 16 f16 (one K step) = 8 packed 32-bit columns
-                    // V: 16 K rows (kv) per step = 2 KB
-                    const uint64_t vb = v_desc + static_cast<uint64_t>(k * (2048 >> 4));
-                    umma_f16_ts(tmem_base + O_COL, tmem_base + P_COL + k * 8, vb, idesc_pv, (j | k) != 0);
+                    for (int k = 0; k < BKV / 16; ++k) {
+                        // P is the A operand straight from TMEM: lane = query row, 16 f16 (one K step) = 8 packed 32-bit columns
+                        // V: 16 K rows (kv) per step = 2 KB
+                        const uint64_t vb = v_desc + static_cast<uint64_t>(k * (2048 >> 4));
+                        umma_f16_ts(tmem_base + O_COL, tmem_base + P_COL + k * 8, vb, idesc_pv, (j | k) != 0);
+                    }
+                    umma_commit(pv_done);
+                    umma_commit(&v_empty[g & 1]);
                 }
-                umma_commit(pv_done);
-                umma_commit(&v_empty[g & 1]);
-#ifdef Q2W_ATT_TIMELINE
-                if (tlm_on && g < 40) tlm[g][4] = clock64() - t_start;
-#endif
-                if (++j == n_kv) j = 0;
             }
         }
     } else {
@@ -326,9 +331,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constan
         float prev_inv = 0.f;
         int prev_q0 = 0, prev_h = 0, prev_b = 0;
         const int release_tile = n_kv > 1 ? 1 : 0;   // the tile after which the leader hands the staged Q buffer back to the producer
-        for (int it = 0; it < my_items; ++it) {
+        for (int it = 0;; ++it) {
+            const int item = item_id(it);
+            if (item < 0) break;
+            items_done = it + 1;
             int q0, h, b;
-            item_coords(it, q0, h, b);
+            item_coords(item, q0, h, b);
             float m_used = -INFINITY;   // reference point of P and O, log2 domain
             float l_sum = 0.f;
             for (int j = 0; j < n_kv; ++j, ++g) {
@@ -442,30 +450,25 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constan
             prev_h = h;
             prev_b = b;
         }
-        if (my_items > 0) {   // the last item's epilogue
+        if (items_done > 0) {   // the last item's epilogue
             mbar_wait(pv_done, (g - 1) & 1);
             tc_fence_after();
-            item_epilogue(prev_inv, prev_q0, prev_h, prev_b, (my_items - 1) & 1);
+            item_epilogue(prev_inv, prev_q0, prev_h, prev_b, (items_done - 1) & 1);
             tc_fence_before();
         }
         if (epi_leader) bulk_wait_group<0>();   // shared memory must outlive the last store's reads (and be safe: its writes too)
     }
 
 #ifdef Q2W_ATT_TIMELINE
-    __syncthreads();
-    if (threadIdx.x == 0) {
+    if (warp == 4 && lane == 0) {
         uint32_t smid;
         unsigned long long gt;
         asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
-        printf("cta %d sm %u items %d cycles %lld end_ns %llu\n", (int)blockIdx.x, smid, my_items, clock64() - t_start, gt);
+        printf("cta %d sm %u items %d cycles %lld end_ns %llu\n", (int)blockIdx.x, smid, items_done, clock64() - t_start, gt);
     }
-    if (tl_on) printf("CTA %d: %d items, %lld cycles in total = %lld per item\n", (int)blockIdx.x, my_items, clock64() - t_start, (clock64() - t_start) / my_items);
     if (tl_on)
-        for (int g = 8; g < 16 && g < n_tiles; ++g)
-            printf("mma g%2d: loop top %lld, qk(g+1) issued %lld, p_full %lld, v_full %lld, pv issued %lld\n", g, tlm[g][0], tlm[g][1], tlm[g][2], tlm[g][3], tlm[g][4]);
-    if (tl_on)
-        for (int g = 0; g < 40 && g < n_tiles; ++g)
+        for (int g = 0; g < 40 && g < items_done * n_kv; ++g)
             printf("g%2d top %6lld s_full %6lld (+%4lld) ld %6lld (+%4lld) st_issued %6lld (+%5lld) st_done %6lld (+%4lld) arrive +%lld\n", g, tl[g][0], tl[g][1],
                    tl[g][1] - tl[g][0], tl[g][2], tl[g][2] - tl[g][1], tl[g][3], tl[g][3] - tl[g][2], tl[g][4], tl[g][4] - tl[g][3], tl[g][5] - tl[g][4]);
 #endif
@@ -473,6 +476,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constan
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+    if (threadIdx.x == 0 && atomicAdd(sched + 1, 1) == static_cast<int>(gridDim.x) - 1) {   // last CTA out: every CTA has taken its final id
+        sched[0] = 0;
+        sched[1] = 0;
+        __threadfence();
     }
 }
 
@@ -495,7 +503,8 @@ PFN_encodeTiled get_encode_fn() {
 
 }  // namespace
 
-cudaError_t attention_f16_tcgen05(const __half* qkv, __half* out, int B, int T, int H, cudaStream_t st) {
+cudaError_t attention_f16_tcgen05(const __half* qkv, __half* out, int B, int T, int H, int* sched, cudaStream_t st) {
+    if (!sched) return cudaErrorInvalidValue;
     if (B <= 0 || T <= 0 || H <= 0) return cudaErrorInvalidValue;
     const int D = H * HD;
     PFN_encodeTiled enc = get_encode_fn();
@@ -532,7 +541,7 @@ cudaError_t attention_f16_tcgen05(const __half* qkv, __half* out, int B, int T, 
     if (items > 0x7fffffffLL / ((T + BKV - 1) / BKV)) return cudaErrorInvalidValue;
     const int n_items = static_cast<int>(items);
     const int grid = n_items < 2 * num_sms ? n_items : 2 * num_sms;   // persistent: two CTAs per SM
-    return launch_pdl(attention_tc_kernel, dim3(grid), dim3(THREADS), SMEM_BYTES, st, tm, tm_out, T, D, n_qt, H, n_items);
+    return launch_pdl(attention_tc_kernel, dim3(grid), dim3(THREADS), SMEM_BYTES, st, tm, tm_out, T, D, n_qt, H, n_items, sched);
 }
 
 }  // namespace q2w

@@ -16,6 +16,7 @@
 #include <cstring>
 #include <map>
 #include <string>
+#include <mutex>
 #include <vector>
 
 using namespace q2w;
@@ -117,6 +118,7 @@ struct q2w_state {
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
     float* logmel = nullptr;   // [B, n_mel, ld_mel]
     float* winmax = nullptr;   // [B] ordered int keys
+    int* att_sched = nullptr;  // [2] work counter of the persistent attention kernel (zero between launches)
     // results
     float* emb = nullptr;      // [n_windows, T/2, D]
     size_t emb_cap_windows = 0;
@@ -289,7 +291,7 @@ int forward_eager(q2w_state* s, int Bm, int w0) {
         // softmax(Q K^T) V per head   (:2080-2106)
         {
             ProfScope ps(s, PC_ATTN, 4.0 * Bm * static_cast<double>(T) * T * D, 8.0 * M * D);
-            CKL(attention_f16_tcgen05(s->qkv, s->att, Bm, T, H, s->stream));
+            CKL(attention_f16_tcgen05(s->qkv, s->att, Bm, T, H, s->att_sched, s->stream));
         }
         // out-proj + bias + residual   (:2112-2120)
         if ((rc = weight_gemm(s, s->att, D, L.o_w.d, m->wtype_dev, M, D, D, static_cast<const float*>(L.o_b.d), s->x, D,
@@ -552,6 +554,8 @@ int q2w_state_create(q2w_state** out, q2w_model* m, int max_batch) {
     SALLOC(s->logmel, B * s->n_mel * s->ld_mel * sizeof(float));
     SALLOC(s->winmax, B * sizeof(float));
     SALLOC(s->api_max, sizeof(float));
+    SALLOC(s->att_sched, 2 * sizeof(int));
+    if (e == cudaSuccess) e = cudaMemset(s->att_sched, 0, 2 * sizeof(int));
 #undef SALLOC
     if (e != cudaSuccess) {
         q2w_state_free(s);
@@ -566,7 +570,7 @@ void q2w_state_free(q2w_state* s) {
     cudaSetDevice(s->m->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
     void* ptrs[] = {s->x, s->ln, s->qkv, s->att, s->h, s->wscratch, s->pcm_dev, s->nsamp_dev, s->logmel, s->winmax,
-                    s->emb, s->api_mel, s->api_pcm, s->api_max};
+                    s->emb, s->api_mel, s->api_pcm, s->api_max, s->att_sched};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& r : s->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     if (s->g1) cudaGraphExecDestroy(s->g1);
@@ -896,7 +900,20 @@ int q2w_op_pool_layernorm(const float* x, const float* gamma, const float* beta,
 }
 
 int q2w_op_attention(const void* qkv, void* out, int B, int T, int H, void* stream) {
-    CKL(attention_f16_tcgen05(static_cast<const __half*>(qkv), static_cast<__half*>(out), B, T, H, static_cast<cudaStream_t>(stream)));
+    // stand-alone op (tests, tools): one work counter per device, so callers on one device must not overlap launches of this op
+    static std::mutex mu;
+    static int* sched[64] = {};
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return fail(Q2W_E_INVALID, "device index out of range");
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        if (!sched[dev]) {
+            CK(cudaMalloc(reinterpret_cast<void**>(&sched[dev]), 2 * sizeof(int)));
+            CK(cudaMemset(sched[dev], 0, 2 * sizeof(int)));
+        }
+    }
+    CKL(attention_f16_tcgen05(static_cast<const __half*>(qkv), static_cast<__half*>(out), B, T, H, sched[dev], static_cast<cudaStream_t>(stream)));
     return Q2W_OK;
 }
 

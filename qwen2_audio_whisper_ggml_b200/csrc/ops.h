@@ -42,7 +42,8 @@ cudaError_t pool2_layernorm_f32(const float* x, const float* gamma, const float*
                                 float eps, cudaStream_t st);
 
 // ---- attention (non-causal, no mask, Q pre-scaled): qkv f16 [B*T, 3*D] (q | k | v blocks of D = H*64), out f16 [B*T, D]
-cudaError_t attention_f16_tcgen05(const __half* qkv, __half* out, int B, int T, int H, cudaStream_t st);
+// sched: two ints of device memory, zero before the first launch (the kernel leaves them zero again); one buffer per stream
+cudaError_t attention_f16_tcgen05(const __half* qkv, __half* out, int B, int T, int H, int* sched, cudaStream_t st);
 // round-1 bring-up kernel (mma.sync + cp.async): kept only as the "recompiled legacy tensor path" baseline the tests and
 // profiles compare against; the engine never calls it
 cudaError_t attention_f16(const __half* qkv, __half* out, int B, int T, int H, cudaStream_t st);
