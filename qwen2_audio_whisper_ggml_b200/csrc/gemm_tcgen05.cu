@@ -29,6 +29,7 @@
 #include "ptx.cuh"
 
 #include <atomic>
+#include <cstdio>
 #include <mutex>
 
 namespace q2w {
@@ -212,13 +213,29 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
+#ifdef Q2W_GEMM_TIMELINE
+            long long t_full = 0, t_acc = 0, n_slow = 0;
+            const long long t_begin = clock64();
+#endif
             for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+#ifdef Q2W_GEMM_TIMELINE
+                long long w0 = clock64();
+#endif
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
                 tc_fence_after();
+#ifdef Q2W_GEMM_TIMELINE
+                t_acc += clock64() - w0;
+#endif
                 const uint32_t d_tmem = tmem_base + acc * BN;
                 for (int kb = 0; kb < nkb; ++kb) {
+#ifdef Q2W_GEMM_TIMELINE
+                    w0 = clock64();
+#endif
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
+#ifdef Q2W_GEMM_TIMELINE
+                    { const long long dt = clock64() - w0; t_full += dt; if (dt > 200) ++n_slow; }
+#endif
                     const uint32_t a_addr = smem_u32(smem + stage * STAGE_BYTES);
                     const uint64_t a_desc = make_sw128_kmajor_desc(a_addr);
                     const uint64_t b_desc = make_sw128_kmajor_desc(a_addr + A_BYTES);
@@ -232,6 +249,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1;
             }
+#ifdef Q2W_GEMM_TIMELINE
+            if (cluster_id == 3) {
+                const long long tot = clock64() - t_begin;
+                const int my_tiles = (num_tiles - cluster_id + num_clusters - 1) / num_clusters;
+                printf("gemm M-tiles %d N-tiles %d K %d: MMA thread %lld clk for %d tiles (%lld per tile, MMA floor %d); waiting for operands %lld (%.1f %%, %lld k-blocks > 200 clk), for a free accumulator %lld (%.1f %%)\n",
+                       p.m_tiles, p.n_tiles, p.K, tot, my_tiles, tot / my_tiles, nkb * 512, t_full, 100.0 * t_full / tot, n_slow, t_acc, 100.0 * t_acc / tot);
+            }
+#endif
         }
         __syncwarp();
     } else if (WT != WT_F16 && warp >= 2 + EPI_WARPS) {
