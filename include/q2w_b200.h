@@ -94,6 +94,13 @@ Q2W_API int  q2w_encode_batch_host(q2w_state* s, const float* pcm_host, size_t s
 Q2W_API int  q2w_encode_batch_device(q2w_state* s, const float* pcm_dev, size_t stride, const int32_t* n_samples_host,
                                      int B);
 
+/* Asynchronous host batches: queue a batch and return; at most two are in flight per state (a third submit first waits for the oldest).
+ * pcm_host / out_host must stay valid (and should be pinned) until q2w_encode_batch_wait(ticket) returns. Lets a caller overlap the
+ * H2D / D2H copies of one batch with the compute of the next -- what a serving loop over whisper_encode_batch would do. */
+Q2W_API int  q2w_encode_batch_host_async(q2w_state* s, const float* pcm_host, size_t stride, const int32_t* n_samples, int B, float* out_host,
+                                         int* ticket);
+Q2W_API int  q2w_encode_batch_wait(q2w_state* s, int ticket);
+
 /* Whole-file streaming: n windows of the state's (globally normalised) mel, starting at the given frame offsets,
  * encoded as one batch -- the batched form of n x whisper_full(ctx, {offset_ms}, NULL, 0)  (:2349-2369). */
 Q2W_API int  q2w_encode_offsets(q2w_state* s, const int32_t* mel_offsets, int n, float* out_host);

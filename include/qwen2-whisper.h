@@ -203,6 +203,10 @@ WHISPER_API int whisper_get_mel(struct whisper_context * ctx, float * dst, size_
  * per-window mel + encoder, results [B][n_out][n_state] copied to dst if non-NULL.  max windows per micro-batch is
  * set once with whisper_set_max_batch (default 16). */
 WHISPER_API int whisper_encode_batch(struct whisper_context * ctx, const float * samples, size_t stride, const int32_t * n_samples, int n_windows, float * dst);
+/* asynchronous form: returns a ticket (>= 0) as soon as the batch is queued, -1 on error; samples / dst must stay valid (pinned for
+ * real overlap) until whisper_encode_batch_wait(ticket) returns 0. At most two batches are in flight per context. */
+WHISPER_API int whisper_encode_batch_async(struct whisper_context * ctx, const float * samples, size_t stride, const int32_t * n_samples, int n_windows, float * dst);
+WHISPER_API int whisper_encode_batch_wait(struct whisper_context * ctx, int ticket);
 WHISPER_API int whisper_encode_batch_device(struct whisper_context * ctx, const float * samples_dev, size_t stride, const int32_t * n_samples, int n_windows);
 /* whole-file streaming: after ONE whisper_pcm_to_mel over the full audio (global normalisation), encode n windows starting at the
  * given mel-frame offsets (offset_ms / 10) as a batch == n x whisper_full(ctx, {offset_ms}, NULL, 0) of the reference */

@@ -77,6 +77,8 @@ _WSIGS = {
     "whisper_encode_batch_device": (_i, [_vp, _vp, _sz, _vp, _i]),
     "whisper_set_max_batch": (_i, [_vp, _i]),
     "whisper_encode_offsets": (_i, [_vp, _vp, _i, _vp]),
+    "whisper_encode_batch_async": (_i, [_vp, _vp, C.c_size_t, _vp, _i, _vp]),
+    "whisper_encode_batch_wait": (_i, [_vp, _i]),
     "whisper_q2w_state": (_vp, [_vp]),
 }
 _bound = False
@@ -231,6 +233,21 @@ class Context:
         if rc != 0:
             raise _l.Q2WError(rc, "whisper_encode_batch failed (see log)")
         return out
+
+    def encode_batch_async(self, windows: np.ndarray, out: np.ndarray, n_samples=None) -> int:
+        """Queue a batch and return a ticket; `windows` and `out` (float32, C-contiguous, ideally pinned) must stay alive and untouched
+        until wait(ticket). Two batches may be in flight: submit i + 1, then wait for i."""
+        assert windows.dtype == np.float32 and windows.flags.c_contiguous and out.dtype == np.float32 and out.flags.c_contiguous
+        B, stride = windows.shape
+        ns = None if n_samples is None else np.ascontiguousarray(n_samples, dtype=np.int32)
+        t = wlib().whisper_encode_batch_async(self._h, windows.ctypes.data, stride, None if ns is None else ns.ctypes.data, B, out.ctypes.data)
+        if t < 0:
+            raise _l.Q2WError(t, "whisper_encode_batch_async failed (see log)")
+        return t
+
+    def wait(self, ticket: int) -> None:
+        if wlib().whisper_encode_batch_wait(self._h, ticket) != 0:
+            raise _l.Q2WError(-1, "whisper_encode_batch_wait failed (see log)")
 
     def encode_long(self, samples, out: np.ndarray | None = None) -> np.ndarray:
         """Audio of any length: cut into 30 s windows (the last one ragged), each with its own mel normalisation, and run

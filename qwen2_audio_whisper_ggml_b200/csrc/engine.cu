@@ -119,6 +119,14 @@ struct q2w_state {
     float* logmel = nullptr;   // [B, n_mel, ld_mel]
     float* winmax = nullptr;   // [B] ordered int keys
     int* att_sched = nullptr;  // [2] work counter of the persistent attention kernel (zero between launches)
+    // asynchronous host batches: at most two in flight; ticket t owns embedding region t & 1 and completion event ev_ticket[t & 1]
+    cudaEvent_t ev_ticket[2] = {nullptr, nullptr};
+    int ticket_B[2] = {0, 0};
+    int64_t ticket_t0[2] = {0, 0};
+    bool ticket_live[2] = {false, false};
+    int next_ticket = 0;
+    size_t emb_off_windows = 0;     // where the embeddings of the last completed call start inside emb
+    uint64_t mb_seq = 0;            // running micro-batch index: staging slot = mb_seq & 1, across calls
     // results
     float* emb = nullptr;      // [n_windows, T/2, D]
     size_t emb_cap_windows = 0;
@@ -326,6 +334,31 @@ int ensure_emb(q2w_state* s, int n_windows) {
         CK(cudaMalloc(&s->emb, static_cast<size_t>(n_windows) * (s->T / 2) * s->D * sizeof(float)));
         s->emb_cap_windows = n_windows;
     }
+    return Q2W_OK;
+}
+
+int ticket_wait(q2w_state* s, int ticket) {
+    const int r = ticket & 1;
+    if (ticket < 0 || !s->ticket_live[r] || (s->next_ticket - ticket) > 2 || ticket >= s->next_ticket)
+        return fail(Q2W_E_INVALID, "ticket %d is not in flight", ticket);
+    CK(cudaSetDevice(s->m->device));
+    CK(cudaEventSynchronize(s->ev_ticket[r]));
+    s->ticket_live[r] = false;
+    s->emb_windows = s->ticket_B[r];
+    s->emb_off_windows = static_cast<size_t>(r) * s->emb_cap_windows / 2;
+    s->t_encode_us += now_us() - s->ticket_t0[r];
+    s->n_encode += s->ticket_B[r];
+    return Q2W_OK;
+}
+
+// waits for every asynchronous batch still in flight
+int drain_tickets(q2w_state* s) {
+    for (int r = 0; r < 2; ++r)
+        if (s->ticket_live[r]) {
+            const int t = (s->next_ticket - 1 - ((s->next_ticket - 1 - r) & 1));
+            int rc = ticket_wait(s, t);
+            if (rc) return rc;
+        }
     return Q2W_OK;
 }
 
@@ -550,6 +583,7 @@ int q2w_state_create(q2w_state** out, q2w_model* m, int max_batch) {
     for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
         e = cudaEventCreateWithFlags(&s->ev_in[i], cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_done[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_ticket[i], cudaEventDisableTiming);
     }
     SALLOC(s->logmel, B * s->n_mel * s->ld_mel * sizeof(float));
     SALLOC(s->winmax, B * sizeof(float));
@@ -574,7 +608,11 @@ void q2w_state_free(q2w_state* s) {
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& r : s->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     if (s->g1) cudaGraphExecDestroy(s->g1);
-    for (int i = 0; i < 2; ++i) { if (s->ev_in[i]) cudaEventDestroy(s->ev_in[i]); if (s->ev_done[i]) cudaEventDestroy(s->ev_done[i]); }
+    for (int i = 0; i < 2; ++i) {
+        if (s->ev_in[i]) cudaEventDestroy(s->ev_in[i]);
+        if (s->ev_done[i]) cudaEventDestroy(s->ev_done[i]);
+        if (s->ev_ticket[i]) cudaEventDestroy(s->ev_ticket[i]);
+    }
     if (s->s_in) cudaStreamDestroy(s->s_in);
     if (s->s_out) cudaStreamDestroy(s->s_out);
     if (s->stream) cudaStreamDestroy(s->stream);
@@ -649,8 +687,10 @@ int q2w_encode(q2w_state* s, int mel_offset) {
     if (mel_offset < 0) return fail(Q2W_E_INVALID, "negative mel offset");
     CK(cudaSetDevice(s->m->device));
     const int64_t t0 = now_us();
-    int rc = ensure_emb(s, 1);
+    int rc = drain_tickets(s);
     if (rc) return rc;
+    if ((rc = ensure_emb(s, 1))) return rc;
+    s->emb_off_windows = 0;
     // window [offset, offset + 2*n_ctx) of the (already normalised) mel, zero past n_len   (:2264-2285)
     CKL(mel_to_conv1_operand(s->api_mel, s->api_ld, s->api_n_len, s->n_mel, nullptr, 0, mel_offset, s->T2, 1, s->att, s->stream));
     if ((rc = forward_from_a1(s, 1, 0))) return rc;
@@ -671,8 +711,10 @@ int q2w_encode_offsets(q2w_state* s, const int32_t* mel_offsets, int n, float* o
         if (mel_offsets[i] < 0) return fail(Q2W_E_INVALID, "negative mel offset");
     CK(cudaSetDevice(s->m->device));
     const int64_t t0 = now_us();
-    int rc = ensure_emb(s, n);
+    int rc = drain_tickets(s);
     if (rc) return rc;
+    if ((rc = ensure_emb(s, n))) return rc;
+    s->emb_off_windows = 0;
     const size_t a1_per_window = static_cast<size_t>(s->T2) * 3 * s->n_mel;
     const size_t out_per_window = static_cast<size_t>(s->T / 2) * s->D;
     for (int w0 = 0; w0 < n; w0 += s->max_batch) {
@@ -692,14 +734,29 @@ int q2w_encode_offsets(q2w_state* s, const int32_t* mel_offsets, int n, float* o
     return Q2W_OK;
 }
 
+// async_ticket == nullptr: synchronous (returns when the embeddings are on the host / device).
+// async_ticket != nullptr: returns as soon as the work is queued; *async_ticket identifies the batch for q2w_encode_batch_wait.
 static int encode_batch_impl(q2w_state* s, const float* pcm, bool pcm_on_host, size_t stride, const int32_t* n_samples, int B,
-                             float* out_host) {
+                             float* out_host, int* async_ticket) {
     if (!s || !pcm || B <= 0) return fail(Q2W_E_INVALID, "bad argument");
     if (stride == 0) return fail(Q2W_E_INVALID, "stride must be > 0");
+    if (async_ticket && !out_host) return fail(Q2W_E_INVALID, "an asynchronous batch needs a host output buffer");
     CK(cudaSetDevice(s->m->device));
     const int64_t t0 = now_us();
-    int rc = ensure_emb(s, B);
-    if (rc) return rc;
+    int rc;
+    int region = 0;
+    if (async_ticket) {
+        region = s->next_ticket & 1;
+        if (s->ticket_live[region] && (rc = ticket_wait(s, s->next_ticket - 2))) return rc;   // at most two batches in flight
+        if (2 * static_cast<size_t>(B) > s->emb_cap_windows) {                                 // growing the buffer: nothing may be in flight
+            if ((rc = drain_tickets(s))) return rc;
+            if ((rc = ensure_emb(s, 2 * B))) return rc;
+        }
+    } else {
+        if ((rc = drain_tickets(s))) return rc;
+        if ((rc = ensure_emb(s, B))) return rc;
+    }
+    const size_t emb_base = static_cast<size_t>(region) * (s->emb_cap_windows / 2);   // in windows
     const size_t width = std::min(stride, static_cast<size_t>(s->win_samples));
     std::vector<int> ns(B);
     for (int b = 0; b < B; ++b) {
@@ -711,21 +768,20 @@ static int encode_batch_impl(q2w_state* s, const float* pcm, bool pcm_on_host, s
     // micro-batches: at most max_batch windows each.  With host buffers a batch that would fit in one micro-batch is still cut
     // in two, so the H2D copy of the second half and the D2H copy of the first half's embeddings overlap compute.
     int mb = std::min(s->max_batch, B);
-    if (pcm_on_host && B <= s->max_batch && B >= 16) {
+    if (pcm_on_host && !async_ticket && B <= s->max_batch && B >= 16) {   // (queued batches overlap with each other instead: no cut)
         static int split = -1;
         if (split < 0) { const char* e = getenv("Q2W_E2E_SPLIT"); split = e ? std::max(1, atoi(e)) : 2; }
         mb = (B + split - 1) / split;
     }
-    int it = 0;
-    for (int w0 = 0; w0 < B; w0 += mb, ++it) {
+    for (int w0 = 0; w0 < B; w0 += mb, ++s->mb_seq) {
         const int Bm = std::min(mb, B - w0);
-        const int slot = it & 1;
+        const int slot = static_cast<int>(s->mb_seq & 1);
         int* nsamp = s->nsamp_dev + static_cast<size_t>(slot) * s->max_batch;
         const float* pcm_dev = nullptr;
         size_t dev_stride = stride;
         if (pcm_on_host) {
             float* stage = s->pcm_dev + static_cast<size_t>(slot) * s->max_batch * s->win_samples;
-            if (it >= 2) CK(cudaStreamWaitEvent(s->s_in, s->ev_done[slot], 0));   // compute of micro-batch it-2 has consumed this slot
+            if (s->mb_seq >= 2) CK(cudaStreamWaitEvent(s->s_in, s->ev_done[slot], 0));   // compute of micro-batch mb_seq - 2 has consumed this slot
             CK(cudaMemcpyAsync(nsamp, ns.data() + w0, sizeof(int) * Bm, cudaMemcpyHostToDevice, s->s_in));
             CK(cudaMemcpy2DAsync(stage, static_cast<size_t>(s->win_samples) * sizeof(float), pcm + static_cast<size_t>(w0) * stride,
                                  stride * sizeof(float), width * sizeof(float), Bm, cudaMemcpyHostToDevice, s->s_in));
@@ -734,32 +790,51 @@ static int encode_batch_impl(q2w_state* s, const float* pcm, bool pcm_on_host, s
             pcm_dev = stage;
             dev_stride = s->win_samples;
         } else {
-            if (it >= 2) CK(cudaStreamWaitEvent(s->stream, s->ev_done[slot], 0));
+            if (s->mb_seq >= 2) CK(cudaStreamWaitEvent(s->stream, s->ev_done[slot], 0));
             CK(cudaMemcpyAsync(nsamp, ns.data() + w0, sizeof(int) * Bm, cudaMemcpyHostToDevice, s->stream));
             pcm_dev = pcm + static_cast<size_t>(w0) * stride;
         }
-        if ((rc = batch_chunk(s, pcm_dev, dev_stride, nsamp, Bm, w0))) return rc;
+        if ((rc = batch_chunk(s, pcm_dev, dev_stride, nsamp, Bm, static_cast<int>(emb_base) + w0))) return rc;
         CK(cudaEventRecord(s->ev_done[slot], s->stream));
         if (out_host) {
             CK(cudaStreamWaitEvent(s->s_out, s->ev_done[slot], 0));
-            CK(cudaMemcpyAsync(out_host + static_cast<size_t>(w0) * out_per_window, s->emb + static_cast<size_t>(w0) * out_per_window,
+            CK(cudaMemcpyAsync(out_host + static_cast<size_t>(w0) * out_per_window, s->emb + (emb_base + w0) * out_per_window,
                                static_cast<size_t>(Bm) * out_per_window * sizeof(float), cudaMemcpyDeviceToHost, s->s_out));
         }
+    }
+    if (async_ticket) {
+        CK(cudaEventRecord(s->ev_ticket[region], s->s_out));   // after the last D2H, which itself waits for the last micro-batch
+        s->ticket_live[region] = true;
+        s->ticket_B[region] = B;
+        s->ticket_t0[region] = t0;
+        *async_ticket = s->next_ticket++;
+        return Q2W_OK;
     }
     if (out_host) CK(cudaStreamSynchronize(s->s_out));
     CK(cudaStreamSynchronize(s->stream));
     s->emb_windows = B;
+    s->emb_off_windows = 0;
     s->t_encode_us += now_us() - t0;
     s->n_encode += B;
     return Q2W_OK;
 }
 
 int q2w_encode_batch_host(q2w_state* s, const float* pcm_host, size_t stride, const int32_t* n_samples, int B, float* out_host) {
-    return encode_batch_impl(s, pcm_host, true, stride, n_samples, B, out_host);
+    return encode_batch_impl(s, pcm_host, true, stride, n_samples, B, out_host, nullptr);
 }
 
 int q2w_encode_batch_device(q2w_state* s, const float* pcm_dev, size_t stride, const int32_t* n_samples_host, int B) {
-    return encode_batch_impl(s, pcm_dev, false, stride, n_samples_host, B, nullptr);
+    return encode_batch_impl(s, pcm_dev, false, stride, n_samples_host, B, nullptr, nullptr);
+}
+
+int q2w_encode_batch_host_async(q2w_state* s, const float* pcm_host, size_t stride, const int32_t* n_samples, int B, float* out_host, int* ticket) {
+    if (!ticket) return fail(Q2W_E_INVALID, "null ticket");
+    return encode_batch_impl(s, pcm_host, true, stride, n_samples, B, out_host, ticket);
+}
+
+int q2w_encode_batch_wait(q2w_state* s, int ticket) {
+    if (!s) return fail(Q2W_E_INVALID, "null argument");
+    return ticket_wait(s, ticket);
 }
 
 int q2w_embd_dims(const q2w_state* s, int* n_windows, int* n_out, int* n_state) {
@@ -775,12 +850,13 @@ int q2w_get_embeddings(q2w_state* s, float* out_host, size_t offset_floats, size
     const size_t total = static_cast<size_t>(s->emb_windows) * (s->T / 2) * s->D;
     if (!s->emb || offset_floats + n_floats > total) return fail(Q2W_E_INVALID, "embedding range [%zu, %zu) outside the %zu floats available", offset_floats, offset_floats + n_floats, total);
     CK(cudaSetDevice(s->m->device));
-    CK(cudaMemcpyAsync(out_host, s->emb + offset_floats, n_floats * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaMemcpyAsync(out_host, s->emb + s->emb_off_windows * (s->T / 2) * s->D + offset_floats, n_floats * sizeof(float), cudaMemcpyDeviceToHost,
+                       s->stream));
     CK(cudaStreamSynchronize(s->stream));
     return Q2W_OK;
 }
 
-const float* q2w_embeddings_device(const q2w_state* s) { return s ? s->emb : nullptr; }
+const float* q2w_embeddings_device(const q2w_state* s) { return s && s->emb ? s->emb + s->emb_off_windows * (s->T / 2) * s->D : nullptr; }
 
 int q2w_get_batch_mel(q2w_state* s, int window, float* out_host) {
     if (!s || !out_host) return fail(Q2W_E_INVALID, "null argument");

@@ -50,6 +50,8 @@ _SIGS = {
     "q2w_encode_batch_host": (_i, [_vp, _vp, _sz, _vp, _i, _vp]),
     "q2w_encode_batch_device": (_i, [_vp, _vp, _sz, _vp, _i]),
     "q2w_encode_offsets": (_i, [_vp, _vp, _i, _vp]),
+    "q2w_encode_batch_host_async": (_i, [_vp, _vp, C.c_size_t, _vp, _i, _vp, _vp]),
+    "q2w_encode_batch_wait": (_i, [_vp, _i]),
     "q2w_embd_dims": (_i, [_vp, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
     "q2w_get_embeddings": (_i, [_vp, _vp, _sz, _sz]),
     "q2w_embeddings_device": (_vp, [_vp]),

@@ -345,3 +345,39 @@ def test_whole_file_streaming_matches_reference_offsets(ref):
     assert out2.shape[0] == 8 and np.array_equal(out2[0], out[0]) and np.array_equal(out2[2], out[1])
     ctx.free()
     rctx.free()
+
+
+def test_async_batches_pipeline_and_match_the_synchronous_call():
+    """whisper_encode_batch_async / _wait: two batches in flight, a third submit first retires the oldest; results are bit-identical
+    to whisper_encode_batch, and the accessors follow the last batch waited for"""
+    import torch
+    ctx, _ = tiny_ctx("f16", seed=9)
+    win = 2 * ctx.model_n("n_audio_ctx") * 160
+    n_out, n_state = ctx.model_n("n_audio_ctx") // 2, ctx.model_n("n_audio_state")
+    B = 20                                                                   # >= 16: the host path cuts it into two micro-batches
+    ctx.set_max_batch(B)
+    batches = [np.stack([synth.synth_pcm(win, seed=100 * k + w, kind="chirp") for w in range(B)]) for k in range(3)]
+    want = [ctx.encode_batch(b).copy() for b in batches]
+    ins = [torch.from_numpy(b).pin_memory() for b in batches]
+    outs = [torch.full((B, n_out, n_state), float("nan")).pin_memory() for _ in range(3)]
+    t0 = ctx.encode_batch_async(ins[0].numpy(), outs[0].numpy())
+    t1 = ctx.encode_batch_async(ins[1].numpy(), outs[1].numpy())
+    t2 = ctx.encode_batch_async(ins[2].numpy(), outs[2].numpy())              # retires t0 internally
+    assert (t0, t1, t2) == (0, 1, 2)
+    with pytest.raises(Exception):
+        ctx.wait(t0)                                                         # already retired
+    ctx.wait(t1)
+    assert np.array_equal(ctx.get_embeddings(), want[1])                     # accessors: the batch just waited for
+    ctx.wait(t2)
+    for k in range(3):
+        assert np.array_equal(outs[k].numpy(), want[k]), k
+    assert np.array_equal(ctx.get_embeddings(), want[2])
+    with pytest.raises(Exception):
+        ctx.wait(7)
+    # a synchronous call drains whatever is in flight and still works
+    t3 = ctx.encode_batch_async(ins[0].numpy(), outs[0].numpy())
+    again = ctx.encode_batch(batches[1])
+    assert np.array_equal(again, want[1]) and np.array_equal(outs[0].numpy(), want[0])
+    with pytest.raises(Exception):
+        ctx.wait(t3)                                                         # drained by the synchronous call
+    ctx.free()
