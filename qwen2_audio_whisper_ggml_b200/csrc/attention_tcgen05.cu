@@ -208,7 +208,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constan
             // take the next item, wait until the Q buffer (and id slot) of item it - 2 is really retired, publish, start the Q load
             auto next_item = [&](int it) {
                 // every CTA's first item is its own index (no round trip before the first loads); the counter hands out the rest
-                const int id = it == 0 ? static_cast<int>(blockIdx.x) : static_cast<int>(gridDim.x) + atomicAdd(sched, 1);
+                // (and when the grid already covers every item there is nothing to hand out: no round trip at all)
+                const int id = it == 0 ? static_cast<int>(blockIdx.x)
+                               : static_cast<int>(gridDim.x) >= n_items ? n_items : static_cast<int>(gridDim.x) + atomicAdd(sched, 1);
                 const int qb = it & 1;
                 if (it >= 2) {
                     mbar_wait(&q_empty[qb], ((it >> 1) - 1) & 1);   // QKs of item it - 2 done with the buffer
