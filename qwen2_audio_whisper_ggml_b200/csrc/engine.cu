@@ -603,6 +603,8 @@ void q2w_state_free(q2w_state* s) {
     if (!s) return;
     cudaSetDevice(s->m->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
+    if (s->s_in) cudaStreamSynchronize(s->s_in);      // asynchronous batches may still be copying from / into caller memory
+    if (s->s_out) cudaStreamSynchronize(s->s_out);
     void* ptrs[] = {s->x, s->ln, s->qkv, s->att, s->h, s->wscratch, s->pcm_dev, s->nsamp_dev, s->logmel, s->winmax,
                     s->emb, s->api_mel, s->api_pcm, s->api_max, s->att_sched};
     for (void* p : ptrs) if (p) cudaFree(p);
