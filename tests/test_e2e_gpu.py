@@ -381,3 +381,32 @@ def test_async_batches_pipeline_and_match_the_synchronous_call():
     with pytest.raises(Exception):
         ctx.wait(t3)                                                         # drained by the synchronous call
     ctx.free()
+
+
+def test_full_size_batch64_is_permutation_equivariant_and_shardable():
+    """BASELINE configs[1] scale (full model, 64 x 30 s windows): size-independent properties of the data-parallel path --
+    permuting the windows permutes the embeddings bit for bit, and any contiguous shard of the batch (what another rank would
+    be given) reproduces its slice bit for bit; every output row is a LayerNorm output (finite, unit variance against gamma = 1 +- small)"""
+    buf = mfm.to_bytes(synth.synth_model(synth.FULL_HPARAMS, WT["f16"], seed=1234))
+    ctx = Context.init_from_buffer(buf)
+    del buf
+    B = 64
+    ctx.set_max_batch(B)
+    rng = np.random.default_rng(5)
+    base = [synth.synth_pcm(480000, seed=200 + k, kind="chirp" if k % 2 else "noise") for k in range(8)]
+    win = np.stack([np.roll(base[w % 8], 997 * w) * (0.25 + 0.75 * rng.random()) for w in range(B)]).astype(np.float32)
+    ns = np.full(B, 480000, dtype=np.int32)
+    ns[7], ns[40], ns[63] = 16000, 250001, 479999                      # ragged windows inside the batch
+    out = ctx.encode_batch(win, ns)
+    assert out.shape == (B, 750, 1280) and np.isfinite(out).all()
+    perm = rng.permutation(B)
+    out_p = ctx.encode_batch(np.ascontiguousarray(win[perm]), ns[perm])
+    assert np.array_equal(out_p, out[perm])
+    from qwen2_audio_whisper_ggml_b200.parallel import shard_bounds
+    for rank in (0, 2):                                                 # 3-way sharding: 22 / 21 / 21 windows
+        lo, hi = shard_bounds(B, rank, 3)
+        assert np.array_equal(ctx.encode_batch(np.ascontiguousarray(win[lo:hi]), ns[lo:hi]), out[lo:hi]), rank
+    assert len({out[w].tobytes() for w in range(B)}) == B              # no two windows collapsed onto each other
+    v = out.reshape(-1, 1280).var(axis=1)
+    assert 0.5 < float(v.min()) and float(v.max()) < 2.0, (v.min(), v.max())
+    ctx.free()
