@@ -19,10 +19,11 @@
 //             to dequantize_row_q8_0 / q4_0 followed by an F16 store) and writes the 128-byte row into the SWIZZLE_128B tile
 //             the MMA reads; the smem stage becomes "full" when the A bytes of both CTAs AND the 8 decode warps have arrived.
 //   warps 2-9 epilogue, two per TMEM lane quadrant.  Everything stays in the "lane = output row" domain the accumulator
-//             arrives in: tcgen05.ld -> bias (broadcast loads) / scale / GELU in registers -> residual added from a tile the
-//             warp TMA-loaded two chunks earlier -> result written in place into the 128B-swizzled smem chunk -> one TMA
-//             store per 32-row chunk.  No per-element global address arithmetic, no predication: M/N tails are clipped by
-//             the TMA unit on store and zero-filled on load.  (Round-1 profiles: the per-element LDG/STG epilogue spent
+//             arrives in: tcgen05.ld -> bias (broadcast loads) / scale / GELU in registers -> result written into the
+//             128B-swizzled smem chunk -> one TMA store per 32-row chunk; the residual epilogue issues a TMA *reduction* store
+//             instead (cp.reduce.async.bulk.tensor ... add: out += acc + bias, summed at L2 -- exactly one add per element, so
+//             still deterministic), which keeps the residual tile off the SM altogether.  No per-element global address
+//             arithmetic, no predication: M/N tails are clipped by the TMA unit on store and zero-filled on load.  (Round-1 profiles: the per-element LDG/STG epilogue spent
 //             ~45 % of its issue slots on 64-bit address math and kept the K = 1280 GEMMs at 45-55 % tensor-pipe activity.)
 #include "ops.h"
 #include "launch.cuh"
@@ -39,12 +40,20 @@ namespace {
 constexpr int BM = 128;            // rows per CTA (256 per pair)
 constexpr int BN = 256;            // columns per pair tile; each CTA stages BN/2 rows of W
 constexpr int BK = 64;
-// smem budget (227 KB): F16-output epilogues need only 2 chunk buffers per warp (no residual prefetch) and get a 5-stage ring;
-// the residual epilogues keep 3 buffers (2 residual tiles in flight + 1 draining) and a 4-stage ring
+// smem budget (227 KB): 2 chunk buffers per epilogue warp and a 5-stage ring. The residual epilogue is a TMA *reduction* store
+// (out += acc + bias, added at L2): no residual tile ever travels to the SM, so it needs no third buffer either.
+// -DQ2W_GEMM_RESID_LOAD restores the previous scheme for A/B runs: residual chunks TMA-loaded two ahead into a 3-buffer rotation,
+// which leaves room for only 4 stages -- measured 22 % (fc2) / 34 % (out-proj) of the main loop waiting for operands.
+#ifdef Q2W_GEMM_RESID_LOAD
+constexpr bool kResidLoad = true;
+#else
+constexpr bool kResidLoad = false;
+#endif
 template <int EPI> struct Cfg {
     static constexpr bool F16OUT = (EPI == EPI_BIAS_F16 || EPI == EPI_BIAS_GELU_F16);
-    static constexpr int STAGES = F16OUT ? 5 : 4;
-    static constexpr int EPI_BUFS = F16OUT ? 2 : 3;
+    static constexpr bool RLOAD = kResidLoad && EPI == EPI_BIAS_RESID_F32;
+    static constexpr int STAGES = RLOAD ? 4 : 5;
+    static constexpr int EPI_BUFS = RLOAD ? 3 : 2;
 };
 constexpr int A_BYTES = BM * BK * 2;          // 16 KB
 constexpr int B_BYTES = (BN / 2) * BK * 2;    // 16 KB (this CTA's half of W)
@@ -161,7 +170,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
         tma_prefetch_desc(&tmO);
-        if constexpr (EPI == EPI_BIAS_RESID_F32) tma_prefetch_desc(&tmR);
+        if constexpr (Cfg<EPI>::RLOAD) tma_prefetch_desc(&tmR);
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full_bar[s], WT == WT_F16 ? 1 : 1 + 2 * DQ_WARPS);   // producer's expect_tx (+ decode warps of both CTAs)
             mbar_init(&empty_bar[s], 1);
@@ -310,7 +319,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         uint8_t* bufs = epi_smem + ew * (EPI_BUFS * CHUNK_BYTES);
         uint64_t* my_rbar = rbar + ew * EPI_BUFS;
         constexpr bool F16OUT = (EPI == EPI_BIAS_F16 || EPI == EPI_BIAS_GELU_F16);
-        constexpr bool RESID = (EPI == EPI_BIAS_RESID_F32);
+        constexpr bool RESID = Cfg<EPI>::RLOAD;                        // residual chunks loaded into the SM (A/B build only)
+        constexpr bool REDUCE = (EPI == EPI_BIAS_RESID_F32) && !RESID;  // out += v through a TMA reduction store
         constexpr int CCOLS = F16OUT ? 64 : 32;    // columns per 128-byte chunk row
         constexpr int CHUNKS = (BN / 2) / CCOLS;   // chunks per warp per tile
         const uint32_t row_off = static_cast<uint32_t>(lane) * 128;
@@ -439,7 +449,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) {
-                    if (n < p.N) tma_store_2d(&tmO, buf, n, m0);   // rows >= M / columns >= N are clipped by the TMA unit
+                    if (n < p.N) {                                  // rows >= M / columns >= N are clipped by the TMA unit
+                        if constexpr (REDUCE) tma_reduce_add_2d(&tmO, buf, n, m0);
+                        else tma_store_2d(&tmO, buf, n, m0);
+                    }
                     bulk_commit_group();
                     if constexpr (RESID) {
                         // the buffer of chunk gc+2 was last read by the store of chunk gc-1: wait for it, then prefetch into it
@@ -549,6 +562,7 @@ cudaError_t gemm_f16_tcgen05(const GemmArgs& a, GemmEpilogue epi, cudaStream_t s
     tmR = tmO;
     if (epi == EPI_BIAS_RESID_F32) {
         if (!a.resid) return cudaErrorInvalidValue;
+        if (!kResidLoad && a.resid != a.out) return cudaErrorInvalidValue;   // the residual epilogue accumulates into `out`: it must BE the residual
         if (reinterpret_cast<uintptr_t>(a.resid) & 15) return cudaErrorMisalignedAddress;
         if (!make_tmap_2d(&tmR, a.resid, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a.M, a.N, a.ldo, 32, 32)) return cudaErrorInvalidValue;
     }
