@@ -242,6 +242,19 @@ def main():
             prev = t
         ctx.wait(prev)
 
+    # ---- single-window latency (p50 ms per 30 s window, B = 1), device-resident PCM. Measured FIRST: it is clock-bound, and right
+    #      after the power-capped throughput phase the SM clock is still held down (4.1 ms here vs 5.2 ms measured afterwards)
+    lat = []
+    for i in range(23):
+        barrier() if i == 0 else None
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record(stream)
+        ctx.encode_batch_device(dev.data_ptr(), 480000, 1)
+        a1.record(stream)
+        torch.cuda.synchronize()
+        if i >= 3:
+            lat.append(a0.elapsed_time(a1))
+
     # ---- device-resident throughput ("value") with the live per-kernel roofline
     for _ in range(a.warmup):
         step_device()
@@ -277,18 +290,6 @@ def main():
     run_host_steps(a.steps)
     barrier()
     e2e_s = time.perf_counter() - t0
-
-    # ---- single-window latency (p50 ms per 30 s window, B = 1), device-resident PCM
-    lat = []
-    for i in range(23):
-        barrier() if i == 0 else None
-        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a0.record(stream)
-        ctx.encode_batch_device(dev.data_ptr(), 480000, 1)
-        a1.record(stream)
-        torch.cuda.synchronize()
-        if i >= 3:
-            lat.append(a0.elapsed_time(a1))
 
     # ---- optional: gather every rank's embeddings on rank 0 over NCCL (the only collective this path ever issues; NOT part of
     #      the timed region -- SURVEY 8(e): "NCCL only to gather embeddings when a caller asks for them on one device")
