@@ -322,8 +322,9 @@ def main():
     roofline = {"bound": "tensor", "kernel": "gemm_kernel<EPI> (tcgen05.mma kind::f16, TMA, TMEM)", "achieved": gemm_tflops, "peak": pk["tflops"],
                 "unit": "TFLOP/s", "frac": gemm_tflops / pk["tflops"], "peak_source": f"{pk['src']} bf16_tflops_sustained (kernel timed inside a long step)",
                 # DRAM bytes per launch (dram__bytes_read + write, ncu --set full, averaged over the four per-layer shapes at M = 96000:
-                # out-proj 1.18 GB, fc1 1.19 GB, fc2 2.24 GB measured, QKV 0.99 GB algorithmic) vs 1.36 GB algorithmic: no wasted re-reads
-                "traffic": 1.40e9 if (a.wtype == "f16" and B == 64) else None, "traffic_unit": "bytes/launch", "traffic_source": "profiles/r01_final_ncu_summary.json",
+                # out-proj 1.17 GB, fc1 1.19 GB, fc2 2.08 GB measured, QKV 0.99 GB algorithmic) vs 1.36 GB algorithmic: no wasted re-reads
+                "traffic": 1.36e9 if (a.wtype == "f16" and B == 64) else None, "traffic_unit": "bytes/launch",
+                "traffic_source": "profiles/r01_gemm_fc2_reduce_epilogue_ncu_summary.json (out-proj, fc2), profiles/r01_final_ncu_summary.json (fc1)",
                 "launches": g["count"], "avg_launch_ms": g["ms"] / max(1, g["count"]),
                 "flops_per_launch": g["flops"] / max(1, g["count"]), "share_of_step": g["ms"] / dev_ms}
     kernels = {}
