@@ -7,7 +7,8 @@
 // row sum; it is evaluated online in FP32, probabilities are rounded to F16 for the PV product, FP32 accumulation.
 //
 // Persistent kernel, two CTAs per SM (256 TMEM columns each), 256 threads per CTA. A work item = 128 query rows of one (window, head);
-// CTA c walks items c, c + gridDim.x, ...; the KV tile sequence is continuous across items, so nothing drains at an item boundary.
+// CTA c starts with item c and pulls the rest from a global counter (both CTAs of an SM finish together); the KV tile sequence is
+// continuous across items, so nothing drains at an item boundary.
 //   warp 0      TMA producer: Q (two buffers, the next item's Q half an item ahead), K_g / V_g tiles (128 x 64 f16, SWIZZLE_128B, two
 //               stages each) through a 3-D tensor map over qkv[B][T][3D] -- rows past T are out of bounds for the map and arrive as
 //               zeros, never as the next window
@@ -117,8 +118,8 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, ui
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
-// Persistent: grid = 2 CTAs per SM, each CTA walks work items (window, head, 128-query tile) with stride gridDim.x. The KV tile
-// sequence is continuous across items (global tile index g): the producer prefetches the next item's Q (two Q buffers) and its
+// Persistent: grid = 2 CTAs per SM; each CTA starts with work item blockIdx.x (window, head, 128-query tile) and pulls every further
+// item from a global counter. The KV tile sequence is continuous across items (global tile index g): the producer prefetches the next item's Q (two Q buffers) and its
 // first K/V tiles while the current item's last tiles are still in the softmax, and the MMA warp issues S = Q' K_0'^T of the next
 // item under the current item's last exp phase -- so TMEM allocation, barrier setup, descriptor fetch and the first TMA round trip
 // (a third of a one-item CTA's lifetime, measured) are paid once per CTA instead of once per item.
