@@ -338,6 +338,13 @@ def main():
             kernels[nm]["gbs"] = p["bytes"] / (p["ms"] * 1e-3) / 1e9
             kernels[nm]["hbm_frac"] = kernels[nm]["gbs"] / pk["hbm_gbs"]
 
+    if "attention" in kernels and clocks.get("sm_mhz"):
+        # at head dim 64 one exponential carries 4 * 64 tensor FLOPs and the SM retires 16 ex2 per clock (tools/ubench/xu_pipe.cu), so the
+        # MUFU, not the tensor pipe, bounds this kernel: ceiling = 148 SMs * 16 * clock * 256 FLOP
+        ceil = 148 * 16 * clocks["sm_mhz"] * 1e6 * 256 / 1e12
+        kernels["attention"]["mufu_ceiling_tflops_at_sampled_clock"] = ceil
+        kernels["attention"]["frac_of_mufu_ceiling"] = kernels["attention"]["tflops"] / ceil
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         try:
