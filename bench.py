@@ -363,7 +363,7 @@ def main():
                         "ms_per_step": 1e3 * e2e_s / a.steps,
                         "api": "whisper_encode_batch (blocking)" if os.environ.get("Q2W_BENCH_E2E_SYNC") == "1" else "whisper_encode_batch_async + whisper_encode_batch_wait, two batches in flight"},
                 "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline, "kernels": kernels,
-                "p50_ms_per_window_b1": statistics.median(lat), "ms_per_window": dev_ms / a.steps / B,
+                "p50_ms_per_window_b1": statistics.median(lat), "p10_p90_ms_per_window_b1": [sorted(lat)[len(lat) // 10], sorted(lat)[(9 * len(lat)) // 10]], "ms_per_window": dev_ms / a.steps / B,
                 "nccl_gather_ms": gather_ms, "setup_s": setup_s}
         line["tflops_whole_step"] = 2.2738e12 * B * a.steps / (dev_ms / 1e3) / 1e12
         print(json.dumps(line))
