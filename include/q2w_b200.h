@@ -62,6 +62,7 @@ Q2W_API int  q2w_model_upload_tensor(q2w_model* m, const char* name, int ggml_ty
 /* all 7 + 15*L tensors present? (:1861)  Builds the fused QKV weight views. */
 Q2W_API int  q2w_model_finalize(q2w_model* m);
 Q2W_API void q2w_model_free(q2w_model* m);
+Q2W_API int  q2w_model_device(const q2w_model* m);
 Q2W_API int  q2w_model_n_tensors_expected(const q2w_model* m);
 Q2W_API int  q2w_model_n_tensors_loaded(const q2w_model* m);
 Q2W_API size_t q2w_model_weight_bytes(const q2w_model* m);
@@ -70,6 +71,10 @@ Q2W_API size_t q2w_model_weight_bytes(const q2w_model* m);
 /* max_batch: windows processed per micro-batch (workspace is sized for it; larger batches are chunked). */
 Q2W_API int  q2w_state_create(q2w_state** out, q2w_model* m, int max_batch);
 Q2W_API void q2w_state_free(q2w_state* s);
+/* resize the per-batch scratch in place: the state's mel, embeddings, timers and streams survive (a state is otherwise what
+ * whisper_init_state builds once, :2779) */
+Q2W_API int  q2w_state_set_max_batch(q2w_state* s, int max_batch);
+Q2W_API int  q2w_state_max_batch(const q2w_state* s);
 
 /* PCM (host, float [-1,1], 16 kHz) -> log-mel kept on the device in the reference's layout float[n_mel][n_len],
  * n_len = (n_samples + 480000) / 160.  Replaces log_mel_spectrogram via whisper_pcm_to_mel_with_state (:3268, :2575). */
@@ -124,6 +129,34 @@ Q2W_API int  q2w_profile_read(q2w_state* s, int kernel_class, double* total_ms, 
 Q2W_API void* q2w_state_stream(const q2w_state* s);
 Q2W_API int  q2w_sync(q2w_state* s);
 
+/* ---- all GPUs of the box from one process (SURVEY 8(b) additive item 3, 8(e)) -------------------- */
+/* One weight replica per device (the caller creates and uploads one q2w_model per device; the same device may be listed more than
+ * once -- replicas are independent), one state + one host worker thread per replica.  A batch is cut into contiguous blocks, window
+ * w -> replica floor(w * G / B); there is no collective on the compute path.  Results land in caller order in out_host (if non-NULL)
+ * and stay on the producing devices; gather_device >= 0 additionally assembles all B x [n_out][n_state] embeddings, ordered by window
+ * index, in one buffer on that device (peer copies over NVLink; q2w_multi_gathered_device).  The reference picks ONE device
+ * (whisper_context_params.gpu_device, include/qwen2-whisper.h:118); this is the "-1 = all visible" extension. */
+typedef struct q2w_multi q2w_multi;
+Q2W_API int  q2w_multi_create(q2w_multi** out, q2w_model* const* models, int n_models, int max_batch_per_device);
+Q2W_API void q2w_multi_free(q2w_multi* mm);                       /* frees the states and workers, NOT the models */
+Q2W_API int  q2w_multi_n_devices(const q2w_multi* mm);
+Q2W_API int  q2w_multi_device(const q2w_multi* mm, int i);        /* CUDA ordinal of replica i */
+Q2W_API q2w_state* q2w_multi_state(q2w_multi* mm, int i);         /* replica i's state (single-window API, accessors) */
+Q2W_API int  q2w_multi_shard_bounds(const q2w_multi* mm, int B, int i, int* lo, int* hi);
+Q2W_API int  q2w_multi_set_max_batch(q2w_multi* mm, int max_batch_per_device);
+Q2W_API int  q2w_multi_encode_batch_host(q2w_multi* mm, const float* pcm_host, size_t stride, const int32_t* n_samples, int B,
+                                         float* out_host, int gather_device /* -1: no gather */);
+Q2W_API const float* q2w_multi_gathered_device(const q2w_multi* mm);
+Q2W_API int  q2w_multi_get_gathered(q2w_multi* mm, float* out_host, size_t n_floats);
+Q2W_API double q2w_multi_last_device_ms(const q2w_multi* mm, int i);   /* device time of replica i's last shard (CUDA events) */
+
+/* ---- stage taps for the parity tests (drift must be localisable) ---------------------- */
+/* stop every following forward pass after n_layers encoder blocks (0 = conv stem + positional embedding only; -1 = all, default);
+ * q2w_debug_get_residual then copies the F32 residual stream x[n_audio_ctx][n_audio_state] of one window of the last forward:
+ * the reference's `cur` / `inpL` at the same point of whisper_build_graph_encoder (:2005, :2154). */
+Q2W_API int  q2w_debug_forward_layers(q2w_state* s, int n_layers);
+Q2W_API int  q2w_debug_get_residual(q2w_state* s, int window, float* out_host);
+
 /* ---- diagnostics -------------------------------------------------------------------------------- */
 Q2W_API const char* q2w_last_error(void);
 Q2W_API long q2w_kernel_launches(void);      /* number of this library's kernels launched so far (bench "gpu_launches") */
@@ -142,10 +175,14 @@ Q2W_API int q2w_op_layernorm(const float* x, const float* gamma, const float* be
 Q2W_API int q2w_op_pool_layernorm(const float* x, const float* gamma, const float* beta, float* y, int B, int T, int D,
                                   float eps, void* stream);
 Q2W_API int q2w_op_attention(const void* qkv_f16, void* out_f16, int B, int T, int H, void* stream);
-/* the mma.sync bring-up kernel, kept as the legacy-tensor-path baseline for tests / profiles only (never on the product path) */
-Q2W_API int q2w_op_attention_legacy_mma(const void* qkv_f16, void* out_f16, int B, int T, int H, void* stream);
 Q2W_API int q2w_op_dequant(const void* src, int ggml_type, void* dst_f16, size_t rows, int K, void* stream);
 Q2W_API int q2w_op_conv2_im2col(const void* h1_f16, void* A2_f16, int B, int T2, int C, void* stream);
+/* window slice [offset, offset + n_ctx2) of B mel-major log-mels (zero past n_frames_valid, :2274-2283), optional clamp/normalise from
+ * the per-window ordered-int max keys, conv1 im2col layout: A1 f16 [B * n_ctx2][3 * n_mel], column = ic * 3 + k */
+Q2W_API int q2w_op_conv1_operand(const float* mel_dev, int ld_frames, int n_frames_valid, int n_mel, const void* win_max_keys_dev,
+                                 int normalise, int offset, int n_ctx2, int B, void* A1_f16, void* stream);
+/* split-K of the residual-epilogue GEMM at small M: 0 off (bit-reproducible single pass), 1 whole k-ranges, 2 balanced, -1 default */
+Q2W_API void q2w_op_set_gemm_splitk(int mode);
 /* mel: filters host [n_mel][201]; pcm device; logmel device [B][n_mel][ld]; win_max device int32[B] (ordered keys) */
 Q2W_API int q2w_op_mel(const float* filters_host, int n_mel, const float* pcm_dev, size_t stride, const int32_t* n_samples_dev,
                        int n_max, int B, int n_frames, float* logmel_dev, int ld, void* win_max_dev, int normalise,

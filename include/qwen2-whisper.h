@@ -85,6 +85,13 @@ WHISPER_API struct whisper_context * whisper_init_with_params            (struct
 WHISPER_API struct whisper_context * whisper_init_from_file_with_params_no_state  (const char * path_model, struct whisper_context_params params);
 WHISPER_API struct whisper_context * whisper_init_from_buffer_with_params_no_state(void * buffer, size_t buffer_size, struct whisper_context_params params);
 WHISPER_API struct whisper_context * whisper_init_with_params_no_state            (struct whisper_model_loader * loader, struct whisper_context_params params);
+/* the deprecated default-params spellings (h:151-174, src:3184-3206); still exported so that old callers relink */
+WHISPER_API struct whisper_context * whisper_init_from_file  (const char * path_model);
+WHISPER_API struct whisper_context * whisper_init_from_buffer(void * buffer, size_t buffer_size);
+WHISPER_API struct whisper_context * whisper_init            (struct whisper_model_loader * loader);
+WHISPER_API struct whisper_context * whisper_init_from_file_no_state  (const char * path_model);
+WHISPER_API struct whisper_context * whisper_init_from_buffer_no_state(void * buffer, size_t buffer_size);
+WHISPER_API struct whisper_context * whisper_init_no_state            (struct whisper_model_loader * loader);
 WHISPER_API struct whisper_state   * whisper_init_state(struct whisper_context * ctx);
 WHISPER_API void whisper_free      (struct whisper_context * ctx);
 WHISPER_API void whisper_free_state(struct whisper_state * state);
@@ -211,7 +218,19 @@ WHISPER_API int whisper_encode_batch_device(struct whisper_context * ctx, const 
 /* whole-file streaming: after ONE whisper_pcm_to_mel over the full audio (global normalisation), encode n windows starting at the
  * given mel-frame offsets (offset_ms / 10) as a batch == n x whisper_full(ctx, {offset_ms}, NULL, 0) of the reference */
 WHISPER_API int whisper_encode_offsets(struct whisper_context * ctx, const int32_t * mel_offsets, int n_windows, float * dst);
-WHISPER_API int whisper_set_max_batch(struct whisper_context * ctx, int max_batch);
+WHISPER_API int whisper_set_max_batch(struct whisper_context * ctx, int max_batch);   /* per device; resizes scratch in place, mel + embeddings survive */
+/* ---- every GPU of the box from one process.  whisper_context_params.gpu_device = -1 loads one weight
+ *      replica on every visible sm_100 device (the reference's field picks one device, h:118); the _multi initialisers take an explicit
+ *      list (an ordinal may repeat: independent replicas).  whisper_encode_batch then shards the windows over the replicas, window w ->
+ *      replica floor(w * G / n_windows), no collective; whisper_encode_batch_multi(..., gather_device) additionally gathers all
+ *      embeddings, in window order, on one device (peer copies over NVLink).  The single-window API runs on replica 0. */
+WHISPER_API struct whisper_context * whisper_init_from_file_multi  (const char * path_model, struct whisper_context_params params, const int * devices, int n_devices);
+WHISPER_API struct whisper_context * whisper_init_from_buffer_multi(void * buffer, size_t buffer_size, struct whisper_context_params params, const int * devices, int n_devices);
+WHISPER_API int whisper_n_devices(struct whisper_context * ctx);
+WHISPER_API int whisper_device   (struct whisper_context * ctx, int i);
+WHISPER_API int whisper_encode_batch_multi(struct whisper_context * ctx, const float * samples, size_t stride, const int32_t * n_samples, int n_windows, float * dst, int gather_device);
+WHISPER_API const float * whisper_get_gathered_device(struct whisper_context * ctx);
+WHISPER_API void * whisper_q2w_multi(struct whisper_context * ctx);   /* q2w_multi* (include/q2w_b200.h) or NULL */
 /* the underlying C-ABI state handle (q2w_state*, include/q2w_b200.h) for callers that need streams / device pointers */
 WHISPER_API void * whisper_q2w_state(struct whisper_context * ctx);
 

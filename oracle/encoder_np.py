@@ -110,14 +110,16 @@ class EncoderOracle:
         h = gelu_tanh(conv(h, self.w["conv2.weight"], self.w["conv2.bias"], 2), via)
         return np.ascontiguousarray(h.T)
 
-    def encode(self, mel_win: np.ndarray, return_pre_pool: bool = False) -> np.ndarray:
+    def encode(self, mel_win: np.ndarray, return_pre_pool: bool = False, n_layers: int | None = None) -> np.ndarray:
+        """n_layers: stop after that many encoder blocks (0 = conv stem + positional embedding); with return_pre_pool the residual
+        stream at that point comes back -- `cur` / `inpL` of whisper_build_graph_encoder (:2005, :2154) -- for the stage tests"""
         hp = self.hp
         T, D, H, L = hp["n_audio_ctx"], hp["n_audio_state"], hp["n_audio_head"], hp["n_audio_layer"]
         hd = D // H
         via = self.mode == "ggml"
         x = self.conv_stem(mel_win) + self.w["embed_positions.weight"][:T]
         scale = np.float32(1.0 / np.sqrt(float(hd)))
-        for i in range(L):
+        for i in range(L if n_layers is None else min(L, n_layers)):
             p = f"layers.{i}."
             c = layer_norm(x, self.w[p + "self_attn_layer_norm.weight"], self.w[p + "self_attn_layer_norm.bias"])
             q = (self._matmul(c, p + "self_attn.q_proj.weight") + self.w[p + "self_attn.q_proj.bias"]) * scale

@@ -80,6 +80,17 @@ _WSIGS = {
     "whisper_encode_batch_async": (_i, [_vp, _vp, C.c_size_t, _vp, _i, _vp]),
     "whisper_encode_batch_wait": (_i, [_vp, _i]),
     "whisper_q2w_state": (_vp, [_vp]),
+    "whisper_init_from_file": (_vp, [C.c_char_p]),
+    "whisper_init_from_buffer": (_vp, [_vp, _sz]),
+    "whisper_init_from_file_no_state": (_vp, [C.c_char_p]),
+    "whisper_init_from_buffer_no_state": (_vp, [_vp, _sz]),
+    "whisper_init_from_file_multi": (_vp, [C.c_char_p, ContextParams, C.POINTER(_i), _i]),
+    "whisper_init_from_buffer_multi": (_vp, [_vp, _sz, ContextParams, C.POINTER(_i), _i]),
+    "whisper_n_devices": (_i, [_vp]),
+    "whisper_device": (_i, [_vp, _i]),
+    "whisper_encode_batch_multi": (_i, [_vp, _vp, _sz, _vp, _i, _vp, _i]),
+    "whisper_get_gathered_device": (_vp, [_vp]),
+    "whisper_q2w_multi": (_vp, [_vp]),
 }
 _bound = False
 
@@ -132,9 +143,14 @@ class Context:
         return cls(wlib().whisper_init_from_file_with_params(path.encode(), p))
 
     @classmethod
-    def init_from_buffer(cls, buf: bytes, params: ContextParams | None = None) -> "Context":
+    def init_from_buffer(cls, buf: bytes, params: ContextParams | None = None, devices=None) -> "Context":
+        """devices: explicit list of CUDA ordinals, one weight replica each (whisper_init_from_buffer_multi); None -> params.gpu_device
+        (-1 = every visible sm_100 device)"""
         p = params if params is not None else default_context_params()
         raw = (C.c_char * len(buf)).from_buffer_copy(buf)
+        if devices is not None:
+            d = (_i * len(devices))(*devices)
+            return cls(wlib().whisper_init_from_buffer_multi(C.cast(raw, C.c_void_p), len(buf), p, d, len(devices)))
         return cls(wlib().whisper_init_from_buffer_with_params(C.cast(raw, C.c_void_p), len(buf), p))
 
     def free(self):
@@ -234,6 +250,38 @@ class Context:
             raise _l.Q2WError(rc, "whisper_encode_batch failed (see log)")
         return out
 
+    def n_devices(self) -> int:
+        return wlib().whisper_n_devices(self._h)
+
+    def devices(self) -> list[int]:
+        return [wlib().whisper_device(self._h, i) for i in range(self.n_devices())]
+
+    def encode_batch_multi(self, windows, n_samples=None, out: np.ndarray | None = None, gather_device: int = -1, want_host: bool = True):
+        """whisper_encode_batch_multi: shard over every replica of the context; gather_device >= 0 also assembles all embeddings on that
+        device (gathered_device_ptr / gathered())"""
+        w = windows if (isinstance(windows, np.ndarray) and windows.dtype == np.float32 and windows.flags.c_contiguous) else _f32(windows)
+        B, stride = w.shape
+        ns = None if n_samples is None else np.ascontiguousarray(n_samples, dtype=np.int32)
+        if want_host and out is None:
+            out = np.empty((B, self.model_n("n_audio_ctx") // 2, self.model_n("n_audio_state")), dtype=np.float32)
+        rc = wlib().whisper_encode_batch_multi(self._h, w.ctypes.data, stride, None if ns is None else ns.ctypes.data, B,
+                                               out.ctypes.data if out is not None else None, gather_device)
+        if rc != 0:
+            raise _l.Q2WError(rc, "whisper_encode_batch_multi failed (see log)")
+        return out
+
+    def gathered_device_ptr(self) -> int:
+        return wlib().whisper_get_gathered_device(self._h)
+
+    def gathered(self, B: int) -> np.ndarray:
+        """host copy of the embeddings gathered on one device by the last encode_batch_multi(..., gather_device=k)"""
+        mm = wlib().whisper_q2w_multi(self._h)
+        out = np.empty((B, self.model_n("n_audio_ctx") // 2, self.model_n("n_audio_state")), dtype=np.float32)
+        if not mm:
+            raise _l.Q2WError(-1, "single-device context: nothing was gathered")
+        _l.check(_l.load_library().q2w_multi_get_gathered(mm, out.ctypes.data, out.size))
+        return out
+
     def encode_batch_async(self, windows: np.ndarray, out: np.ndarray, n_samples=None) -> int:
         """Queue a batch and return a ticket; `windows` and `out` (float32, C-contiguous, ideally pinned) must stay alive and untouched
         until wait(ticket). Two batches may be in flight: submit i + 1, then wait for i."""
@@ -281,6 +329,16 @@ class Context:
 
     def q2w_state(self) -> int:
         return wlib().whisper_q2w_state(self._h)
+
+    def debug_forward_layers(self, n_layers: int) -> None:
+        """stage tap (parity tests): every following forward stops after n_layers encoder blocks (-1 = all)"""
+        _l.check(_l.load_library().q2w_debug_forward_layers(self.q2w_state(), n_layers))
+
+    def debug_residual(self, window: int = 0) -> np.ndarray:
+        """F32 residual stream [n_audio_ctx, n_audio_state] of one window of the last forward"""
+        out = np.empty((self.model_n("n_audio_ctx"), self.model_n("n_audio_state")), dtype=np.float32)
+        _l.check(_l.load_library().q2w_debug_get_residual(self.q2w_state(), window, out.ctypes.data))
+        return out
 
     def embeddings_device_ptr(self) -> int:
         return wlib().whisper_get_embeddings_device(self._h)

@@ -32,6 +32,7 @@
 #include "launch.cuh"
 #include "ptx.cuh"
 
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <mutex>
@@ -459,7 +460,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constan
             item_epilogue(prev_inv, prev_q0, prev_h, prev_b, (items_done - 1) & 1);
             tc_fence_before();
         }
-        if (epi_leader) bulk_wait_group<0>();   // shared memory must outlive the last store's reads (and be safe: its writes too)
+        if (epi_leader) bulk_wait_group_read<0>();   // shared memory must outlive the last store's reads; the writes complete with the grid
     }
 
 #ifdef Q2W_ATT_TIMELINE
@@ -531,14 +532,12 @@ cudaError_t attention_f16_tcgen05(const __half* qkv, __half* out, int B, int T, 
                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
             return cudaErrorInvalidValue;
     }
-    static int num_sms = 0;
-    if (num_sms == 0) {
-        cudaError_t err = cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-        if (err != cudaSuccess) return err;
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    }
+    static std::atomic<unsigned long long> configured{0};   // per device (launch.cuh)
+    DeviceInfo di;
+    cudaError_t err = current_device_info(di);
+    if (err != cudaSuccess) return err;
+    if ((err = smem_optin_once(attention_tc_kernel, SMEM_BYTES, di.dev, configured)) != cudaSuccess) return err;
+    const int num_sms = di.num_sms;
     const int n_qt = (T + BQ - 1) / BQ;
     const long long items = static_cast<long long>(n_qt) * H * B;
     if (items > 0x7fffffffLL / ((T + BKV - 1) / BKV)) return cudaErrorInvalidValue;

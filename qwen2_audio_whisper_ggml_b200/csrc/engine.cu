@@ -34,6 +34,12 @@ int fail(int code, const char* fmt, ...) {
     return code;
 }
 
+}  // namespace
+
+int q2w::set_last_error(int code, const char* msg) { return fail(code, "%s", msg ? msg : ""); }
+
+namespace {
+
 #define CK(call)                                                                                       \
     do {                                                                                               \
         cudaError_t e__ = (call);                                                                      \
@@ -119,6 +125,11 @@ struct q2w_state {
     float* logmel = nullptr;   // [B, n_mel, ld_mel]
     float* winmax = nullptr;   // [B] ordered int keys
     int* att_sched = nullptr;  // [2] work counter of the persistent attention kernel (zero between launches)
+    bool att_sched_dirty = false;   // a forward pass failed part-way: re-zero the counter before the next launch
+    int dbg_layers = -1;       // q2w_debug_forward_layers: stop after this many encoder blocks (-1 = all); eager launches only
+    int dbg_windows = 0;       // windows of the last forward still resident in x
+    int fused_dequant = -1;    // Q2W_FUSED_DEQUANT: 1 always in-kernel decode, 0 always scratch, -1 pick by M
+    int e2e_split = 2;         // Q2W_E2E_SPLIT: micro-batches a synchronous host batch is cut into
     // asynchronous host batches: at most two in flight; ticket t owns embedding region t & 1 and completion event ev_ticket[t & 1]
     cudaEvent_t ev_ticket[2] = {nullptr, nullptr};
     int ticket_B[2] = {0, 0};
@@ -198,6 +209,8 @@ struct ProfScope {
     }
     ~ProfScope() { if (idx >= 0) cudaEventRecord(s->prof[idx].b, s->stream); }
 };
+// largest M for which the in-kernel decode beats decode-to-scratch + F16 GEMM (measured at M = 1500: see DESIGN.md section 5)
+constexpr int kFusedDequantMaxM = 0;
 enum { PC_GEMM = 0, PC_ATTN = 1, PC_LN = 2, PC_MEL = 3, PC_IM2COL = 4, PC_DEQUANT = 5, PC_COUNT = 6 };
 
 // y = A x W^T with W in the model's device type: quantised matrices are decoded to f16 into the (L2-resident) scratch first
@@ -207,13 +220,13 @@ int weight_gemm(q2w_state* s, const __half* A, int lda, const void* W, int wtype
     const __half* Wh = static_cast<const __half*>(W);
     int gemm_wtype = Q2W_TYPE_F16;
     if (wtype_dev != Q2W_TYPE_F16) {
-        // Two decode strategies, both keep W quantised in HBM (measured at B = 64 on B200):
-        //   fused   raw ggml blocks go straight into the GEMM and are decoded by its dequant warpgroup (Q2W_FUSED_DEQUANT=1):
-        //           Q8_0 GEMMs 440 TFLOP/s -- every W tile is re-decoded by each of the 750 M-tiles that use it
-        //   scratch one decode pass per GEMM into a 13 MB L2-resident F16 scratch, then the TMA-fed F16 GEMM (default):
-        //           1205 TFLOP/s, the decode pass costs 1 % of the step
-        static int fused = -1;
-        if (fused < 0) { const char* e = getenv("Q2W_FUSED_DEQUANT"); fused = (e && atoi(e) != 0) ? 1 : 0; }
+        // Two decode strategies, both keep W quantised in HBM (measured on B200):
+        //   fused   raw ggml blocks go straight into the GEMM and are decoded by its dequant warpgroup:
+        //           every W tile is re-decoded by each M-tile that uses it -- 2.7x slower at M = 96000 (750 M-tiles per W tile)
+        //   scratch one decode pass per GEMM into a 13 MB L2-resident F16 scratch, then the TMA-fed F16 GEMM:
+        //           1205 TFLOP/s at B = 64, the decode pass costs 1 % of the step
+        // Selected by M (few M-tiles per W tile -> the decode launch and the scratch round trip weigh more); Q2W_FUSED_DEQUANT=0/1 forces one.
+        const bool fused = s->fused_dequant >= 0 ? s->fused_dequant != 0 : M <= kFusedDequantMaxM;
         if (fused && K % 64 == 0) {
             gemm_wtype = wtype_dev;
         } else {
@@ -226,15 +239,30 @@ int weight_gemm(q2w_state* s, const __half* A, int lda, const void* W, int wtype
     GemmArgs g{};
     g.A = A; g.lda = lda; g.W = Wh; g.ldw = K; g.wtype = gemm_wtype; g.M = M; g.N = N; g.K = K; g.bias = bias; g.out = out; g.ldo = ldo;
     g.resid = resid; g.pos = pos; g.pos_period = pos_period; g.scale_cols = scale_cols; g.scale = scale;
+    g.w_static = Wh != s->wscratch;     // model weights are immutable; the decode scratch is written by the kernel just before this one
     CKL(gemm_f16_tcgen05(g, epi, s->stream));
     return Q2W_OK;
 }
 
 int forward_eager(q2w_state* s, int Bm, int w0);
+int forward_dispatch(q2w_state* s, int Bm, int w0);
 
 // conv stem + encoder for Bm windows whose conv1 operand A1 (in s->att) is ready; writes emb rows [w0, w0+Bm)
 int forward_from_a1(q2w_state* s, int Bm, int w0) {
-    if (Bm != 1 || w0 != 0 || s->prof_on || s->g1_state < 0) return forward_eager(s, Bm, w0);
+    if (s->att_sched_dirty) {
+        // a previous pass failed between launches: the attention work counter may be non-zero (the kernel re-zeroes it only when it
+        // runs to completion), which would silently mis-schedule every later launch
+        CK(cudaMemsetAsync(s->att_sched, 0, 2 * sizeof(int), s->stream));
+        s->att_sched_dirty = false;
+    }
+    const int rc = forward_dispatch(s, Bm, w0);
+    if (rc != Q2W_OK) s->att_sched_dirty = true;
+    else s->dbg_windows = Bm;
+    return rc;
+}
+
+int forward_dispatch(q2w_state* s, int Bm, int w0) {
+    if (Bm != 1 || w0 != 0 || s->prof_on || s->g1_state < 0 || s->dbg_layers >= 0) return forward_eager(s, Bm, w0);
     if (s->g1_state == 2 && s->g1_emb == s->emb) {
         CK(cudaGraphLaunch(s->g1, s->stream));
         g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -285,7 +313,8 @@ int forward_eager(q2w_state* s, int Bm, int w0) {
                           s->x, D, EPI_BIAS_GELU_POS_F32, nullptr, static_cast<const float*>(m->pe.d), T, 0, 1.f)))
         return rc;
     const float kq_scale = 1.0f / sqrtf(static_cast<float>(D / H));  // :1985
-    for (int il = 0; il < m->hp.n_audio_layer; ++il) {
+    const int n_layers = s->dbg_layers >= 0 ? std::min(s->dbg_layers, m->hp.n_audio_layer) : m->hp.n_audio_layer;
+    for (int il = 0; il < n_layers; ++il) {
         Layer& L = m->layers[il];
         // pre-LN + fused QKV projection (+bias, Q * KQscale)   (:2019-2055)
         {
@@ -535,6 +564,10 @@ void q2w_model_free(q2w_model* m) {
     cudaSetDevice(m->device);
     for (auto& kv : m->by_name) free_tensor(*kv.second);
     for (auto& ly : m->layers) {
+        // every member, registered by name or not (creation may have failed midway through this layer); free_tensor is idempotent
+        Tensor* ts[] = {&ly.ln1_w, &ly.ln1_b, &ly.q_w, &ly.q_b, &ly.k_w, &ly.v_w, &ly.v_b, &ly.o_w, &ly.o_b, &ly.ln2_w, &ly.ln2_b,
+                        &ly.fc1_w, &ly.fc1_b, &ly.fc2_w, &ly.fc2_b};
+        for (Tensor* t : ts) free_tensor(*t);
         if (ly.qkv_w) cudaFree(ly.qkv_w);
         if (ly.qkv_b) cudaFree(ly.qkv_b);
     }
@@ -546,11 +579,45 @@ void q2w_model_free(q2w_model* m) {
     delete m;
 }
 
+int q2w_model_device(const q2w_model* m) { return m ? m->device : -1; }
 int q2w_model_n_tensors_expected(const q2w_model* m) { return m ? static_cast<int>(m->by_name.size()) : 0; }
 int q2w_model_n_tensors_loaded(const q2w_model* m) { return m ? m->n_loaded : 0; }
 size_t q2w_model_weight_bytes(const q2w_model* m) { return m ? m->weight_bytes : 0; }
 
 // =============================================================================================== state
+// workspaces that scale with max_batch (everything else in the state -- API mel, embeddings, timers, streams -- survives a resize)
+static void free_workspaces(q2w_state* s) {
+    void** ptrs[] = {reinterpret_cast<void**>(&s->x), reinterpret_cast<void**>(&s->ln), reinterpret_cast<void**>(&s->qkv),
+                     reinterpret_cast<void**>(&s->att), reinterpret_cast<void**>(&s->h), reinterpret_cast<void**>(&s->pcm_dev),
+                     reinterpret_cast<void**>(&s->nsamp_dev), reinterpret_cast<void**>(&s->logmel), reinterpret_cast<void**>(&s->winmax)};
+    for (void** p : ptrs) {
+        if (*p) cudaFree(*p);
+        *p = nullptr;
+    }
+    if (s->g1) { cudaGraphExecDestroy(s->g1); s->g1 = nullptr; }
+    s->g1_state = 0;
+    s->dbg_windows = 0;
+}
+
+static cudaError_t alloc_workspaces(q2w_state* s, int max_batch) {
+    const size_t B = max_batch, T = s->T, D = s->D;
+    const size_t att_elems = std::max(T * D, static_cast<size_t>(s->T2) * 3 * s->n_mel);
+    cudaError_t e = cudaSuccess;
+#define SALLOC(ptr, bytes) if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&(ptr)), (bytes))
+    SALLOC(s->x, B * T * D * sizeof(float));
+    SALLOC(s->ln, B * T * D * sizeof(__half));
+    SALLOC(s->qkv, B * T * 3 * D * sizeof(__half));
+    SALLOC(s->att, B * att_elems * sizeof(__half));
+    SALLOC(s->h, B * T * 4 * D * sizeof(__half));
+    SALLOC(s->pcm_dev, 2 * B * s->win_samples * sizeof(float));
+    SALLOC(s->nsamp_dev, 2 * B * sizeof(int));
+    SALLOC(s->logmel, B * s->n_mel * s->ld_mel * sizeof(float));
+    SALLOC(s->winmax, B * sizeof(float));
+#undef SALLOC
+    if (e == cudaSuccess) s->max_batch = max_batch;
+    return e;
+}
+
 int q2w_state_create(q2w_state** out, q2w_model* m, int max_batch) {
     if (!out || !m) return fail(Q2W_E_INVALID, "null argument");
     *out = nullptr;
@@ -565,19 +632,17 @@ int q2w_state_create(q2w_state** out, q2w_model* m, int max_batch) {
     s->win_samples = s->T2 * 160;
     s->n_frames_batch = s->T2 + 2;                      // frames T2, T2+1 still see real samples and enter the max (:2522, :2634)
     s->ld_mel = (s->n_frames_batch + 15) / 16 * 16;
-    const size_t B = max_batch, T = s->T, D = s->D;
-    const size_t att_elems = std::max(T * D, static_cast<size_t>(s->T2) * 3 * s->n_mel);
+    const size_t D = s->D;
     const size_t wmax = std::max<size_t>(static_cast<size_t>(4) * D * D, 3 * D * D);
+    {   // decode strategy for quantised weights, resolved once per state
+        const char* e = getenv("Q2W_FUSED_DEQUANT");
+        s->fused_dequant = e ? atoi(e) : -1;             // -1: pick by M (weight_gemm)
+        const char* sp = getenv("Q2W_E2E_SPLIT");
+        s->e2e_split = sp ? std::max(1, atoi(sp)) : 2;
+    }
     cudaError_t e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
-#define SALLOC(ptr, bytes) if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&(ptr)), (bytes))
-    SALLOC(s->x, B * T * D * sizeof(float));
-    SALLOC(s->ln, B * T * D * sizeof(__half));
-    SALLOC(s->qkv, B * T * 3 * D * sizeof(__half));
-    SALLOC(s->att, B * att_elems * sizeof(__half));
-    SALLOC(s->h, B * T * 4 * D * sizeof(__half));
-    SALLOC(s->wscratch, wmax * sizeof(__half));
-    SALLOC(s->pcm_dev, 2 * B * s->win_samples * sizeof(float));
-    SALLOC(s->nsamp_dev, 2 * B * sizeof(int));
+    if (e == cudaSuccess) e = alloc_workspaces(s, max_batch);
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&s->wscratch), wmax * sizeof(__half));
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->s_in, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->s_out, cudaStreamNonBlocking);
     for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
@@ -585,12 +650,9 @@ int q2w_state_create(q2w_state** out, q2w_model* m, int max_batch) {
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_done[i], cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_ticket[i], cudaEventDisableTiming);
     }
-    SALLOC(s->logmel, B * s->n_mel * s->ld_mel * sizeof(float));
-    SALLOC(s->winmax, B * sizeof(float));
-    SALLOC(s->api_max, sizeof(float));
-    SALLOC(s->att_sched, 2 * sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&s->api_max), sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&s->att_sched), 2 * sizeof(int));
     if (e == cudaSuccess) e = cudaMemset(s->att_sched, 0, 2 * sizeof(int));
-#undef SALLOC
     if (e != cudaSuccess) {
         q2w_state_free(s);
         return fail(e == cudaErrorMemoryAllocation ? Q2W_E_NOMEM : Q2W_E_CUDA, "state allocation failed: %s", cudaGetErrorString(e));
@@ -599,17 +661,44 @@ int q2w_state_create(q2w_state** out, q2w_model* m, int max_batch) {
     return Q2W_OK;
 }
 
+// Resize the per-batch workspaces in place. The state's mel (whisper_pcm_to_mel / whisper_set_mel), its embeddings, timers and
+// streams are kept; only scratch is reallocated (and the captured single-window graph dropped, its buffers are gone).
+int q2w_state_set_max_batch(q2w_state* s, int max_batch) {
+    if (!s) return fail(Q2W_E_INVALID, "null argument");
+    if (max_batch < 1) return fail(Q2W_E_INVALID, "max_batch must be >= 1");
+    if (max_batch == s->max_batch) return Q2W_OK;
+    CK(cudaSetDevice(s->m->device));
+    int rc = drain_tickets(s);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(s->stream));
+    CK(cudaStreamSynchronize(s->s_in));
+    CK(cudaStreamSynchronize(s->s_out));
+    const int old = s->max_batch;
+    free_workspaces(s);
+    cudaError_t e = alloc_workspaces(s, max_batch);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        free_workspaces(s);
+        if (alloc_workspaces(s, old) != cudaSuccess) { cudaGetLastError(); free_workspaces(s); s->max_batch = 0; }
+        return fail(e == cudaErrorMemoryAllocation ? Q2W_E_NOMEM : Q2W_E_CUDA, "workspace allocation for max_batch %d failed: %s", max_batch,
+                    cudaGetErrorString(e));
+    }
+    s->mb_seq = 0;
+    return Q2W_OK;
+}
+
+int q2w_state_max_batch(const q2w_state* s) { return s ? s->max_batch : 0; }
+
 void q2w_state_free(q2w_state* s) {
     if (!s) return;
     cudaSetDevice(s->m->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
     if (s->s_in) cudaStreamSynchronize(s->s_in);      // asynchronous batches may still be copying from / into caller memory
     if (s->s_out) cudaStreamSynchronize(s->s_out);
-    void* ptrs[] = {s->x, s->ln, s->qkv, s->att, s->h, s->wscratch, s->pcm_dev, s->nsamp_dev, s->logmel, s->winmax,
-                    s->emb, s->api_mel, s->api_pcm, s->api_max, s->att_sched};
+    free_workspaces(s);
+    void* ptrs[] = {s->wscratch, s->emb, s->api_mel, s->api_pcm, s->api_max, s->att_sched};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& r : s->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
-    if (s->g1) cudaGraphExecDestroy(s->g1);
     for (int i = 0; i < 2; ++i) {
         if (s->ev_in[i]) cudaEventDestroy(s->ev_in[i]);
         if (s->ev_done[i]) cudaEventDestroy(s->ev_done[i]);
@@ -693,7 +782,8 @@ int q2w_encode(q2w_state* s, int mel_offset) {
     if (rc) return rc;
     if ((rc = ensure_emb(s, 1))) return rc;
     s->emb_off_windows = 0;
-    // window [offset, offset + 2*n_ctx) of the (already normalised) mel, zero past n_len   (:2264-2285)
+    // window [offset, offset + 2*n_ctx) of the (already normalised) mel, zero past n_len   (:2264-2285; i0 = min(mel_offset, n_len))
+    mel_offset = std::min(mel_offset, s->api_n_len);
     CKL(mel_to_conv1_operand(s->api_mel, s->api_ld, s->api_n_len, s->n_mel, nullptr, 0, mel_offset, s->T2, 1, s->att, s->stream));
     if ((rc = forward_from_a1(s, 1, 0))) return rc;
     CK(cudaStreamSynchronize(s->stream));
@@ -722,7 +812,7 @@ int q2w_encode_offsets(q2w_state* s, const int32_t* mel_offsets, int n, float* o
     for (int w0 = 0; w0 < n; w0 += s->max_batch) {
         const int Bm = std::min(s->max_batch, n - w0);
         for (int b = 0; b < Bm; ++b)   // window slice + zero fill past n_len + im2col, one launch per window (same mel, different offset)
-            CKL(mel_to_conv1_operand(s->api_mel, s->api_ld, s->api_n_len, s->n_mel, nullptr, 0, mel_offsets[w0 + b], s->T2, 1,
+            CKL(mel_to_conv1_operand(s->api_mel, s->api_ld, s->api_n_len, s->n_mel, nullptr, 0, std::min(mel_offsets[w0 + b], s->api_n_len), s->T2, 1,
                                      s->att + static_cast<size_t>(b) * a1_per_window, s->stream));
         if ((rc = forward_from_a1(s, Bm, w0))) return rc;
         if (out_host)
@@ -771,9 +861,7 @@ static int encode_batch_impl(q2w_state* s, const float* pcm, bool pcm_on_host, s
     // in two, so the H2D copy of the second half and the D2H copy of the first half's embeddings overlap compute.
     int mb = std::min(s->max_batch, B);
     if (pcm_on_host && !async_ticket && B <= s->max_batch && B >= 16) {   // (queued batches overlap with each other instead: no cut)
-        static int split = -1;
-        if (split < 0) { const char* e = getenv("Q2W_E2E_SPLIT"); split = e ? std::max(1, atoi(e)) : 2; }
-        mb = (B + split - 1) / split;
+        mb = (B + s->e2e_split - 1) / s->e2e_split;
     }
     for (int w0 = 0; w0 < B; w0 += mb, ++s->mb_seq) {
         const int Bm = std::min(mb, B - w0);
@@ -930,6 +1018,23 @@ int q2w_sync(q2w_state* s) {
     return Q2W_OK;
 }
 
+// =============================================================================================== stage taps (parity tests)
+int q2w_debug_forward_layers(q2w_state* s, int n_layers) {
+    if (!s) return fail(Q2W_E_INVALID, "null argument");
+    s->dbg_layers = n_layers < 0 ? -1 : n_layers;
+    return Q2W_OK;
+}
+
+int q2w_debug_get_residual(q2w_state* s, int window, float* out_host) {
+    if (!s || !out_host) return fail(Q2W_E_INVALID, "null argument");
+    if (window < 0 || window >= s->dbg_windows) return fail(Q2W_E_INVALID, "window %d not resident (last forward held %d)", window, s->dbg_windows);
+    CK(cudaSetDevice(s->m->device));
+    const size_t n = static_cast<size_t>(s->T) * s->D;
+    CK(cudaMemcpyAsync(out_host, s->x + static_cast<size_t>(window) * n, n * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    return Q2W_OK;
+}
+
 // =============================================================================================== diagnostics
 const char* q2w_last_error(void) { return g_err; }
 long q2w_kernel_launches(void) { return g_launches.load(); }
@@ -995,11 +1100,6 @@ int q2w_op_attention(const void* qkv, void* out, int B, int T, int H, void* stre
     return Q2W_OK;
 }
 
-int q2w_op_attention_legacy_mma(const void* qkv, void* out, int B, int T, int H, void* stream) {
-    CKL(attention_f16(static_cast<const __half*>(qkv), static_cast<__half*>(out), B, T, H, static_cast<cudaStream_t>(stream)));
-    return Q2W_OK;
-}
-
 int q2w_op_dequant(const void* src, int ggml_type, void* dst, size_t rows, int K, void* stream) {
     CKL(dequant_to_f16(src, ggml_type, static_cast<__half*>(dst), rows, K, static_cast<cudaStream_t>(stream)));
     return Q2W_OK;
@@ -1009,6 +1109,15 @@ int q2w_op_conv2_im2col(const void* h1, void* A2, int B, int T2, int C, void* st
     CKL(conv2_im2col(static_cast<const __half*>(h1), static_cast<__half*>(A2), B, T2, C, static_cast<cudaStream_t>(stream)));
     return Q2W_OK;
 }
+
+int q2w_op_conv1_operand(const float* mel_dev, int ld_frames, int n_frames_valid, int n_mel, const void* win_max_keys_dev, int normalise,
+                          int offset, int n_ctx2, int B, void* A1_f16, void* stream) {
+    CKL(mel_to_conv1_operand(mel_dev, ld_frames, n_frames_valid, n_mel, static_cast<const float*>(win_max_keys_dev), normalise, offset, n_ctx2, B,
+                             static_cast<__half*>(A1_f16), static_cast<cudaStream_t>(stream)));
+    return Q2W_OK;
+}
+
+void q2w_op_set_gemm_splitk(int mode) { gemm_set_splitk_mode(mode); }
 
 int q2w_op_mel(const float* filters_host, int n_mel, const float* pcm_dev, size_t stride, const int32_t* n_samples_dev, int n_max,
                int B, int n_frames, float* logmel_dev, int ld, void* win_max_dev, int normalise, void* stream) {

@@ -31,6 +31,7 @@
 
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <mutex>
 
 namespace q2w {
@@ -41,19 +42,13 @@ constexpr int BM = 128;            // rows per CTA (256 per pair)
 constexpr int BN = 256;            // columns per pair tile; each CTA stages BN/2 rows of W
 constexpr int BK = 64;
 // smem budget (227 KB): 2 chunk buffers per epilogue warp and a 5-stage ring. The residual epilogue is a TMA *reduction* store
-// (out += acc + bias, added at L2): no residual tile ever travels to the SM, so it needs no third buffer either.
-// -DQ2W_GEMM_RESID_LOAD restores the previous scheme for A/B runs: residual chunks TMA-loaded two ahead into a 3-buffer rotation,
-// which leaves room for only 4 stages -- measured 22 % (fc2) / 34 % (out-proj) of the main loop waiting for operands.
-#ifdef Q2W_GEMM_RESID_LOAD
-constexpr bool kResidLoad = true;
-#else
-constexpr bool kResidLoad = false;
-#endif
+// (out += acc + bias, added at L2): no residual tile ever travels to the SM, so it needs no third buffer either (the round-1
+// scheme that TMA-loaded residual chunks into a 3-buffer rotation left room for 4 stages only and measured 22 % (fc2) / 34 %
+// (out-proj) of the main loop waiting for operands; it is gone).
 template <int EPI> struct Cfg {
     static constexpr bool F16OUT = (EPI == EPI_BIAS_F16 || EPI == EPI_BIAS_GELU_F16);
-    static constexpr bool RLOAD = kResidLoad && EPI == EPI_BIAS_RESID_F32;
-    static constexpr int STAGES = RLOAD ? 4 : 5;
-    static constexpr int EPI_BUFS = RLOAD ? 3 : 2;
+    static constexpr int STAGES = 5;
+    static constexpr int EPI_BUFS = 2;
 };
 constexpr int A_BYTES = BM * BK * 2;          // 16 KB
 constexpr int B_BYTES = (BN / 2) * BK * 2;    // 16 KB (this CTA's half of W)
@@ -80,6 +75,47 @@ struct KParams {
     int m_tiles, n_tiles;   // in units of 256 x 256
     const uint8_t* wraw;    // quantised W: raw ggml blocks, row pitch wrow_bytes
     int wrow_bytes;
+    int sk_upc;             // split-K (residual epilogue, small M only): k-block units per cluster; 0 = whole tiles, strided over the clusters
+    int w_static;           // W is a model weight no kernel ever writes: its first tiles may be fetched before griddepcontrol.wait
+};
+
+// Work distribution.  Classic: cluster c owns the whole tiles c, c + C, c + 2C, ...  Split-K (sk_upc > 0): the (tile, k-block) units
+// are numbered tile-major and cluster c owns the contiguous range [c * upc, (c + 1) * upc), cut into per-tile segments; every segment
+// ends in its own reduction-store epilogue (out += partial, summed at L2), the segment that holds k-block 0 also adds the bias.
+// All roles of a cluster (producer, MMA issuer, decode warps, epilogue) enumerate the same segments with this iterator.
+struct WorkIter {
+    int nkb, a, b, step;
+    bool sk;
+    __device__ __forceinline__ WorkIter(const KParams& p, int nkb_, int cluster_id, int num_clusters) {
+        nkb = nkb_;
+        sk = p.sk_upc > 0;
+        const int num_tiles = p.m_tiles * p.n_tiles;
+        if (sk) {
+            a = cluster_id * p.sk_upc;
+            b = min(a + p.sk_upc, num_tiles * nkb);
+            step = 0;
+        } else {
+            a = cluster_id;
+            b = num_tiles;
+            step = num_clusters;
+        }
+    }
+    __device__ __forceinline__ bool next(int& tile, int& kb0, int& kb1) {
+        if (a >= b) return false;
+        if (sk) {
+            tile = a / nkb;
+            kb0 = a - tile * nkb;
+            const int n = min(nkb - kb0, b - a);
+            kb1 = kb0 + n;
+            a += n;
+        } else {
+            tile = a;
+            kb0 = 0;
+            kb1 = nkb;
+            a += step;
+        }
+        return true;
+    }
 };
 
 __device__ __forceinline__ float gelu_tanh(float x) {
@@ -142,7 +178,7 @@ __device__ __forceinline__ void decode_row(const uint32_t (&w)[DqTraits<WT>::WOR
 template <int EPI, int WT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WT == WT_F16 ? NUM_THREADS : NUM_THREADS_Q, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-            const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR, const KParams p) {
+            const __grid_constant__ CUtensorMap tmO, const KParams p) {
     constexpr int STAGES = Cfg<EPI>::STAGES;
     constexpr int EPI_BUFS = Cfg<EPI>::EPI_BUFS;
     constexpr int EPI_BYTES = epi_bytes<EPI>();
@@ -154,8 +190,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     uint64_t* empty_bar = bars + STAGES;             // [STAGES]  one per CTA, released by the leader's multicast commit
     uint64_t* tfull_bar = bars + 2 * STAGES;         // [2]       accumulator ready, multicast to both CTAs
     uint64_t* tempty_bar = bars + 2 * STAGES + 2;    // [2]       leader only: 2 x EPI_WARPS arrivals
-    uint64_t* rbar = bars + 2 * STAGES + 4;          // [EPI_WARPS][EPI_BUFS] residual chunk landed
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rbar + EPI_WARPS * EPI_BUFS);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -163,14 +198,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const bool leader = cta_rank == 0;
     const int cluster_id = blockIdx.x >> 1;
     const int num_clusters = gridDim.x >> 1;
-    const int num_tiles = p.m_tiles * p.n_tiles;
     const int nkb = (p.K + BK - 1) / BK;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
         tma_prefetch_desc(&tmO);
-        if constexpr (Cfg<EPI>::RLOAD) tma_prefetch_desc(&tmR);
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full_bar[s], WT == WT_F16 ? 1 : 1 + 2 * DQ_WARPS);   // producer's expect_tx (+ decode warps of both CTAs)
             mbar_init(&empty_bar[s], 1);
@@ -179,7 +212,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             mbar_init(&tfull_bar[s], 1);
             mbar_init(&tempty_bar[s], 2 * EPI_WARPS);
         }
-        for (int i = 0; i < EPI_WARPS * EPI_BUFS; ++i) mbar_init(&rbar[i], 1);
         fence_mbar_init();
     }
     if (warp == 1) {
@@ -190,6 +222,23 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     cluster_sync_all();          // barrier inits of both CTAs visible before any remote arrive / multicast
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // The weights do not depend on the previous kernel: the W tiles of the first ring pass are requested BEFORE griddepcontrol.wait,
+    // so their HBM round trip runs under the predecessor's tail (weights are read once per forward at small M: always a DRAM miss).
+    int w_early = 0;             // (producer thread) k-blocks whose W tile and expect_tx are already issued
+    if constexpr (WT == WT_F16) {
+        if (warp == 0 && lane == 0 && p.w_static) {
+            WorkIter wi(p, nkb, cluster_id, num_clusters);
+            int tile, kb0, kb1;
+            if (wi.next(tile, kb0, kb1)) {
+                const int n0 = (tile % p.n_tiles) * BN + static_cast<int>(cta_rank) * (BN / 2);
+                w_early = min(STAGES, kb1 - kb0);
+                for (int i = 0; i < w_early; ++i) {
+                    if (leader) mbar_expect_tx(&full_bar[i], 2 * STAGE_BYTES);
+                    tma_load_2d_cta2(smem + i * STAGE_BYTES + A_BYTES, &tmB, smem_u32(&full_bar[i]) & kPeerBitMask, (kb0 + i) * BK, n0);
+                }
+            }
+        }
+    }
     pdl_wait();                  // everything above overlapped the previous kernel's tail; from here on its output is visible
     pdl_launch_dependents();
 
@@ -198,17 +247,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+            int issued = 0;
+            WorkIter wi(p, nkb, cluster_id, num_clusters);
+            int tile, kb0, kb1;
+            while (wi.next(tile, kb0, kb1)) {
                 const int m0 = (tile / p.n_tiles) * (2 * BM) + static_cast<int>(cta_rank) * BM;
                 const int n0 = (tile % p.n_tiles) * BN + static_cast<int>(cta_rank) * (BN / 2);
-                for (int kb = 0; kb < nkb; ++kb) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                for (int kb = kb0; kb < kb1; ++kb, ++issued) {
                     uint8_t* sA = smem + stage * STAGE_BYTES;
                     uint8_t* sB = sA + A_BYTES;
-                    if (leader) mbar_expect_tx(&full_bar[stage], WT == WT_F16 ? 2 * STAGE_BYTES : 2 * A_BYTES);   // TMA bytes of both CTAs
                     const uint32_t full_leader = smem_u32(&full_bar[stage]) & kPeerBitMask;
-                    tma_load_2d_cta2(sA, &tmA, full_leader, kb * BK, m0);
-                    if constexpr (WT == WT_F16) tma_load_2d_cta2(sB, &tmB, full_leader, kb * BK, n0);
+                    if (issued < w_early) {          // first ring pass: stage free by construction, W and the byte count already in flight
+                        tma_load_2d_cta2(sA, &tmA, full_leader, kb * BK, m0);
+                    } else {
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        if (leader) mbar_expect_tx(&full_bar[stage], WT == WT_F16 ? 2 * STAGE_BYTES : 2 * A_BYTES);   // TMA bytes of both CTAs
+                        tma_load_2d_cta2(sA, &tmA, full_leader, kb * BK, m0);
+                        if constexpr (WT == WT_F16) tma_load_2d_cta2(sB, &tmB, full_leader, kb * BK, n0);
+                    }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -224,11 +280,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             uint32_t acc_phase = 0;
 #ifdef Q2W_GEMM_TIMELINE
             long long t_full = 0, t_acc = 0, n_slow = 0;
+            int my_tiles = 0;
             const long long t_begin = clock64();
 #endif
-            for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+            WorkIter wi(p, nkb, cluster_id, num_clusters);
+            int tile, kb0, kb1;
+            while (wi.next(tile, kb0, kb1)) {
 #ifdef Q2W_GEMM_TIMELINE
                 long long w0 = clock64();
+                ++my_tiles;
 #endif
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
                 tc_fence_after();
@@ -236,7 +296,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 t_acc += clock64() - w0;
 #endif
                 const uint32_t d_tmem = tmem_base + acc * BN;
-                for (int kb = 0; kb < nkb; ++kb) {
+                for (int kb = kb0; kb < kb1; ++kb) {
 #ifdef Q2W_GEMM_TIMELINE
                     w0 = clock64();
 #endif
@@ -250,7 +310,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     const uint64_t b_desc = make_sw128_kmajor_desc(a_addr + A_BYTES);
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k)
-                        umma_f16_ss_cta2(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+                        umma_f16_ss_cta2(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb != kb0) || (k != 0));
                     umma_commit_cta2_mcast(&empty_bar[stage], 0x3);   // both CTAs may refill this stage
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -259,10 +319,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 if (acc == 0) acc_phase ^= 1;
             }
 #ifdef Q2W_GEMM_TIMELINE
-            if (cluster_id == 3) {
+            if (cluster_id == 3 && my_tiles > 0) {
                 const long long tot = clock64() - t_begin;
-                const int my_tiles = (num_tiles - cluster_id + num_clusters - 1) / num_clusters;
-                printf("gemm M-tiles %d N-tiles %d K %d: MMA thread %lld clk for %d tiles (%lld per tile, MMA floor %d); waiting for operands %lld (%.1f %%, %lld k-blocks > 200 clk), for a free accumulator %lld (%.1f %%)\n",
+                printf("gemm M-tiles %d N-tiles %d K %d: MMA thread %lld clk for %d segments (%lld per segment, MMA floor %d per whole tile); waiting for operands %lld (%.1f %%, %lld k-blocks > 200 clk), for a free accumulator %lld (%.1f %%)\n",
                        p.m_tiles, p.n_tiles, p.K, tot, my_tiles, tot / my_tiles, nkb * 512, t_full, 100.0 * t_full / tot, n_slow, t_acc, 100.0 * t_acc / tot);
             }
 #endif
@@ -278,7 +337,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const int kblocks = p.K / 32;                                   // ggml blocks per row
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+            WorkIter wi(p, nkb, cluster_id, num_clusters);
+            int tile, kb0, kb1;
+            while (wi.next(tile, kb0, kb1)) {
                 const int n = (tile % p.n_tiles) * BN + static_cast<int>(cta_rank) * (BN / 2) + row;
                 const bool valid = n < p.N;
                 const uint32_t* wrow = reinterpret_cast<const uint32_t*>(p.wraw + static_cast<size_t>(valid ? n : 0) * p.wrow_bytes);
@@ -290,9 +351,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
                     for (int i = 0; i < WORDS; ++i) dst[i] = (valid && (two || i < WORDS / 2 + 1)) ? __ldg(src + i) : 0u;
                 };
-                fetch(0, cur);
-                for (int kb = 0; kb < nkb; ++kb) {
-                    if (kb + 1 < nkb) fetch(kb + 1, nxt);                    // one k-step ahead, overlaps the wait + decode below
+                fetch(kb0, cur);
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    if (kb + 1 < kb1) fetch(kb + 1, nxt);                    // one k-step ahead, overlaps the wait + decode below
                     uint32_t o[32];
                     decode_row<WT>(cur, o);
                     mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -317,42 +378,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int q = warp & 3;                    // TMEM lane quadrant this warp may access
         const int chalf = ew >> 2;                 // which 128-column half of the tile
         uint8_t* bufs = epi_smem + ew * (EPI_BUFS * CHUNK_BYTES);
-        uint64_t* my_rbar = rbar + ew * EPI_BUFS;
         constexpr bool F16OUT = (EPI == EPI_BIAS_F16 || EPI == EPI_BIAS_GELU_F16);
-        constexpr bool RESID = Cfg<EPI>::RLOAD;                        // residual chunks loaded into the SM (A/B build only)
-        constexpr bool REDUCE = (EPI == EPI_BIAS_RESID_F32) && !RESID;  // out += v through a TMA reduction store
+        constexpr bool REDUCE = (EPI == EPI_BIAS_RESID_F32);   // out += v through a TMA reduction store
         constexpr int CCOLS = F16OUT ? 64 : 32;    // columns per 128-byte chunk row
         constexpr int CHUNKS = (BN / 2) / CCOLS;   // chunks per warp per tile
         const uint32_t row_off = static_cast<uint32_t>(lane) * 128;
         const uint32_t sw = static_cast<uint32_t>(lane & 7);
 
-        // chunk gc (running counter over this warp's whole life) -> coordinates
-        auto chunk_coords = [&](long gc, int& m, int& n) -> bool {
-            const long ti = gc / CHUNKS;
-            const int c = static_cast<int>(gc - ti * CHUNKS);
-            const long tile = cluster_id + ti * num_clusters;
-            if (tile >= num_tiles) return false;
-            m = static_cast<int>(tile / p.n_tiles) * (2 * BM) + static_cast<int>(cta_rank) * BM + q * 32;
-            n = static_cast<int>(tile % p.n_tiles) * BN + chalf * (BN / 2) + c * CCOLS;
-            return true;
-        };
-        auto prefetch_resid = [&](long gc) {   // lane 0 only
-            int m, n;
-            if (!chunk_coords(gc, m, n)) return;
-            const int b = static_cast<int>(gc % EPI_BUFS);
-            mbar_expect_tx(&my_rbar[b], CHUNK_BYTES);
-            tma_load_2d(bufs + b * CHUNK_BYTES, &tmR, &my_rbar[b], n, m);
-        };
-
-        long gc = 0;
-        if constexpr (RESID) {
-            if (lane == 0) { prefetch_resid(0); prefetch_resid(1); }
-        }
+        long gc = 0;                               // running chunk counter: buffer rotation
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        WorkIter wi(p, nkb, cluster_id, num_clusters);
+        int tile, kb0, kb1;
+        while (wi.next(tile, kb0, kb1)) {
             const int m0 = (tile / p.n_tiles) * (2 * BM) + static_cast<int>(cta_rank) * BM + q * 32;
             const int nbase = (tile % p.n_tiles) * BN + chalf * (BN / 2);
+            const bool add_bias = p.bias != nullptr && kb0 == 0;   // split-K: only the segment that starts the K range carries the bias
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_row = tmem_base + acc * BN + chalf * (BN / 2) + (static_cast<uint32_t>(q * 32) << 16);
@@ -384,7 +425,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     if (lane == 0) mbar_arrive_cluster(&tempty_bar[acc], 0);
                 }
                 // ---- bias (+ scale / GELU / positional) in registers; the column index is uniform across the warp
-                if (p.bias) {
+                if (add_bias) {
 #pragma unroll
                     for (int g = 0; g < CCOLS / 4; ++g) {
                         if (n + 4 * g < p.N) {
@@ -414,19 +455,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                         }
                     }
                 }
-                // ---- the chunk buffer: wait for the residual rows (RESID) / for the store that last read this buffer
-                if constexpr (RESID) {
-                    mbar_wait(&my_rbar[b], static_cast<uint32_t>((gc / EPI_BUFS) & 1));
-#pragma unroll
-                    for (int g = 0; g < 8; ++g) {
-                        const float4 rv = *reinterpret_cast<const float4*>(buf + row_off + ((static_cast<uint32_t>(g) ^ sw) << 4));
-                        v[4 * g + 0] += rv.x; v[4 * g + 1] += rv.y; v[4 * g + 2] += rv.z; v[4 * g + 3] += rv.w;
-                    }
-                } else {
-                    // buffer b was last read by the store of chunk gc - EPI_BUFS; at most EPI_BUFS - 1 newer groups may still be pending
-                    if (lane == 0) bulk_wait_group_read<EPI_BUFS - 1>();
-                    __syncwarp();
-                }
+                // ---- the chunk buffer: buffer b was last read by the store of chunk gc - EPI_BUFS; at most EPI_BUFS - 1 newer groups may
+                //      still be pending
+                if (lane == 0) bulk_wait_group_read<EPI_BUFS - 1>();
+                __syncwarp();
                 // ---- write the 128-byte row of this chunk, 16-byte pieces XOR-swizzled like SWIZZLE_128B expects
                 if constexpr (F16OUT) {
 #pragma unroll
@@ -454,17 +486,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                         else tma_store_2d(&tmO, buf, n, m0);
                     }
                     bulk_commit_group();
-                    if constexpr (RESID) {
-                        // the buffer of chunk gc+2 was last read by the store of chunk gc-1: wait for it, then prefetch into it
-                        bulk_wait_group_read<1>();
-                        prefetch_resid(gc + 2);
-                    }
                 }
             }
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
         }
-        if (lane == 0) bulk_wait_group<0>();   // all stores complete before the CTA may exit
+        // shared memory must outlive the reads of the last stores; their global writes are ordinary outstanding memory operations of this
+        // grid, complete and visible before any dependent grid passes its griddepcontrol.wait / starts in stream order
+        if (lane == 0) bulk_wait_group_read<0>();
         __syncwarp();
     }
 
@@ -510,33 +539,66 @@ bool make_tmap_2d(CUtensorMap* tm, const void* ptr, CUtensorMapDataType dt, size
 }
 
 std::atomic<int> g_launches{0};
-int g_num_sms = 0;
+
+// split-K policy for the residual epilogue (Q2W_GEMM_SPLITK: 0 = off, 1 = equal whole k-ranges per tile, 2 = balanced unit ranges that may
+// straddle tiles; default 1.  Measured at M = 1500 on B200, graph replay, us per launch: out-proj 13.2 / 10.7 / 13.4, fc2 30.2 / 20.1 / 20.7
+// for modes 0 / 1 / 2 -- the balanced ranges pay a second 256 KB reduction epilogue per cluster for 33 instead of 40 k-blocks)
+std::atomic<int> g_splitk_override{-1};   // gemm_set_splitk_mode(): tests pin the bit-exact single-pass path with 0
+int splitk_mode() {
+    static const int env_mode = [] {
+        const char* e = std::getenv("Q2W_GEMM_SPLITK");
+        return e ? std::atoi(e) : 1;
+    }();
+    const int o = g_splitk_override.load(std::memory_order_relaxed);
+    return o >= 0 ? o : env_mode;
+}
+constexpr int SK_MIN_KB = 16;      // only K >= 1024 is worth cutting (and the tiny test models keep their bit-exact single-pass sums)
+constexpr int SK_MIN_SEG = 4;      // k-blocks per cluster, at least
 
 template <int EPI, int WT>
-cudaError_t launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const CUtensorMap& tmR, const KParams& kp,
-                   cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_kernel<EPI, WT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<EPI>());
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
-    if (g_num_sms == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-    }
+cudaError_t launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, KParams kp, cudaStream_t st) {
+    static std::atomic<unsigned long long> configured{0};
+    DeviceInfo di;
+    cudaError_t e = current_device_info(di);
+    if (e != cudaSuccess) return e;
+    if ((e = smem_optin_once(gemm_kernel<EPI, WT>, smem_bytes<EPI>(), di.dev, configured)) != cudaSuccess) return e;
     const int tiles = kp.m_tiles * kp.n_tiles;
-    const int max_clusters = g_num_sms / 2;
-    const int clusters = tiles < max_clusters ? tiles : max_clusters;
+    const int max_clusters = di.num_sms / 2;
+    int clusters = tiles < max_clusters ? tiles : max_clusters;
+    kp.sk_upc = 0;
+    if constexpr (EPI == EPI_BIAS_RESID_F32) {
+        // Small M leaves most of the machine idle (M = 1500: 30 tiles for 74 CTA pairs, and fc2 runs 80 k-blocks on them). The
+        // epilogue already is `out += partial` at L2, so cutting K costs nothing but the order of the F32 adds: with two or more
+        // partial sums per element the result is no longer bit-reproducible from run to run (differences of one F32 ulp of the
+        // residual stream). That trade is confined to this small-M path: large batches never take it.
+        const int nkb = (kp.K + BK - 1) / BK;
+        const int mode = splitk_mode();
+        if (mode > 0 && nkb >= SK_MIN_KB && 2 * tiles <= max_clusters) {
+            int upc;
+            if (mode == 1) {
+                int split = max_clusters / tiles;
+                while (split > 1 && (nkb % split || nkb / split < SK_MIN_SEG)) --split;
+                upc = nkb / split;
+            } else {
+                const int units = tiles * nkb;
+                upc = (units + max_clusters - 1) / max_clusters;
+                if (upc < SK_MIN_SEG) upc = SK_MIN_SEG;
+            }
+            if (upc < nkb) {
+                kp.sk_upc = upc;
+                clusters = (tiles * nkb + upc - 1) / upc;
+            }
+        }
+    }
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return launch_pdl(gemm_kernel<EPI, WT>, dim3(2 * clusters), dim3(WT == WT_F16 ? NUM_THREADS : NUM_THREADS_Q), smem_bytes<EPI>(), st, tmA, tmB,
-                      tmO, tmR, kp);
+                      tmO, kp);
 }
 
 }  // namespace
 
 int gemm_num_launches() { return g_launches.load(); }
+void gemm_set_splitk_mode(int mode) { g_splitk_override.store(mode, std::memory_order_relaxed); }
 
 cudaError_t gemm_f16_tcgen05(const GemmArgs& a, GemmEpilogue epi, cudaStream_t st) {
     if (a.M <= 0 || a.N <= 0 || a.K <= 0) return cudaErrorInvalidValue;
@@ -544,7 +606,7 @@ cudaError_t gemm_f16_tcgen05(const GemmArgs& a, GemmEpilogue epi, cudaStream_t s
     if ((reinterpret_cast<uintptr_t>(a.A) | reinterpret_cast<uintptr_t>(a.W) | reinterpret_cast<uintptr_t>(a.out)) & 15)
         return cudaErrorMisalignedAddress;
     const bool f16out = (epi == EPI_BIAS_F16 || epi == EPI_BIAS_GELU_F16);
-    CUtensorMap tmA, tmB, tmO, tmR;
+    CUtensorMap tmA, tmB, tmO;
     if (!make_tmap_2d(&tmA, a.A, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, a.M, a.K, a.lda, BM, BK)) return cudaErrorInvalidValue;
     const int wt = a.wtype == 0 ? WT_F16 : a.wtype;
     if (wt != WT_F16 && wt != WT_Q8_0 && wt != WT_Q4_0) return cudaErrorInvalidValue;
@@ -559,13 +621,7 @@ cudaError_t gemm_f16_tcgen05(const GemmArgs& a, GemmEpilogue epi, cudaStream_t s
     } else {
         if (!make_tmap_2d(&tmO, a.out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a.M, a.N, a.ldo, 32, 32)) return cudaErrorInvalidValue;
     }
-    tmR = tmO;
-    if (epi == EPI_BIAS_RESID_F32) {
-        if (!a.resid) return cudaErrorInvalidValue;
-        if (!kResidLoad && a.resid != a.out) return cudaErrorInvalidValue;   // the residual epilogue accumulates into `out`: it must BE the residual
-        if (reinterpret_cast<uintptr_t>(a.resid) & 15) return cudaErrorMisalignedAddress;
-        if (!make_tmap_2d(&tmR, a.resid, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a.M, a.N, a.ldo, 32, 32)) return cudaErrorInvalidValue;
-    }
+    if (epi == EPI_BIAS_RESID_F32 && a.resid != a.out) return cudaErrorInvalidValue;   // the residual epilogue accumulates into `out`: it must BE the residual
     KParams kp;
     kp.M = a.M; kp.N = a.N; kp.K = a.K;
     kp.bias = a.bias;
@@ -575,12 +631,14 @@ cudaError_t gemm_f16_tcgen05(const GemmArgs& a, GemmEpilogue epi, cudaStream_t s
     kp.n_tiles = (a.N + BN - 1) / BN;
     kp.wraw = static_cast<const uint8_t*>(static_cast<const void*>(a.W));
     kp.wrow_bytes = wt == WT_Q8_0 ? a.K / 32 * 34 : wt == WT_Q4_0 ? a.K / 32 * 18 : 0;
+    kp.sk_upc = 0;
+    kp.w_static = a.w_static;
     if (epi == EPI_BIAS_GELU_POS_F32 && !a.pos) return cudaErrorInvalidValue;
 #define Q2W_DISPATCH(E)                                                                 \
     case E:                                                                             \
-        if (wt == WT_F16) return launch<E, WT_F16>(tmA, tmB, tmO, tmR, kp, st);         \
-        if (wt == WT_Q8_0) return launch<E, WT_Q8_0>(tmA, tmB, tmO, tmR, kp, st);       \
-        return launch<E, WT_Q4_0>(tmA, tmB, tmO, tmR, kp, st);
+        if (wt == WT_F16) return launch<E, WT_F16>(tmA, tmB, tmO, kp, st);         \
+        if (wt == WT_Q8_0) return launch<E, WT_Q8_0>(tmA, tmB, tmO, kp, st);       \
+        return launch<E, WT_Q4_0>(tmA, tmB, tmO, kp, st);
     switch (epi) {
         Q2W_DISPATCH(EPI_BIAS_F16)
         Q2W_DISPATCH(EPI_BIAS_GELU_F16)
@@ -588,7 +646,7 @@ cudaError_t gemm_f16_tcgen05(const GemmArgs& a, GemmEpilogue epi, cudaStream_t s
         Q2W_DISPATCH(EPI_BIAS_F32)
         case EPI_BIAS_GELU_POS_F32:     // conv stem only: its kernels are always F16 in the model file (vtype, :1543)
             if (wt != WT_F16) return cudaErrorInvalidValue;
-            return launch<EPI_BIAS_GELU_POS_F32, WT_F16>(tmA, tmB, tmO, tmR, kp, st);
+            return launch<EPI_BIAS_GELU_POS_F32, WT_F16>(tmA, tmB, tmO, kp, st);
     }
 #undef Q2W_DISPATCH
     return cudaErrorInvalidValue;

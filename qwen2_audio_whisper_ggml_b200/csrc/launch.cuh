@@ -4,10 +4,47 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdlib>
 #include <cstring>
 
 namespace q2w {
+
+// Function attributes (the > 48 KB dynamic shared memory opt-in) and the SM count are PER DEVICE: a process may hold contexts on
+// several GPUs (q2w_model_create takes any ordinal, q2w_multi_* drives all of them), so every latch below is keyed by the device
+// that is current at launch time, never by "first call in this process".
+constexpr int kMaxDevices = 64;
+
+struct DeviceInfo {
+    int dev = -1;
+    int num_sms = 0;
+};
+inline cudaError_t current_device_info(DeviceInfo& out) {
+    static std::atomic<int> sms[kMaxDevices] = {};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= kMaxDevices) return cudaErrorInvalidDevice;
+    int n = sms[dev].load(std::memory_order_relaxed);
+    if (n == 0) {
+        e = cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (e != cudaSuccess) return e;
+        sms[dev].store(n, std::memory_order_relaxed);
+    }
+    out.dev = dev;
+    out.num_sms = n;
+    return cudaSuccess;
+}
+
+// one opt-in per (kernel, device); `done` is a per-kernel bit mask owned by the caller (a function-local static)
+template <typename K>
+inline cudaError_t smem_optin_once(K kernel, int bytes, int dev, std::atomic<unsigned long long>& done) {
+    const unsigned long long bit = 1ull << dev;
+    if (done.load(std::memory_order_acquire) & bit) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) done.fetch_or(bit, std::memory_order_release);
+    return e;
+}
 
 inline bool pdl_enabled() {
     static const bool on = [] {

@@ -9,6 +9,9 @@
 
 namespace q2w {
 
+// sets the calling thread's q2w_last_error() text and returns `code` (engine.cu)
+int set_last_error(int code, const char* msg);
+
 // ---- GEMM: out[M,N] = epilogue( A[M,K] (f16, row-major, lda) x W[N,K]^T (f16, row-major, ldw) ), F32 accumulate in TMEM
 enum GemmEpilogue : int {
     EPI_BIAS_F16       = 0,  // out f16 = (acc + bias[n]) * (n < scale_cols ? scale : 1)        (fused QKV projection)
@@ -28,11 +31,16 @@ struct GemmArgs {
     const float* resid;           // [M, ldo] f32 (EPI_BIAS_RESID_F32)
     const float* pos; int pos_period;  // [pos_period, N] f32 (EPI_BIAS_GELU_POS_F32)
     int scale_cols;   float scale;     // EPI_BIAS_F16
+    int w_static;                 // 1: W is a model weight that no kernel writes (never the dequant scratch): the kernel may fetch its first
+                                  // tiles before waiting for the previous kernel in the stream (programmatic dependent launch)
 };
 
 // returns cudaSuccess or the failing error; never aborts
 cudaError_t gemm_f16_tcgen05(const GemmArgs& a, GemmEpilogue epi, cudaStream_t st);
 int gemm_num_launches();  // bookkeeping for bench "gpu_launches"
+// split-K of the residual epilogue at small M: 0 off (bit-reproducible single pass), 1 whole k-ranges per tile, 2 balanced unit
+// ranges, -1 back to the default (env Q2W_GEMM_SPLITK, else 1)
+void gemm_set_splitk_mode(int mode);
 
 // ---- LayerNorm: y f16 [M, D] = (x - mean) * rsqrt(var + eps) * gamma + beta, x f32 [M, D]
 cudaError_t layernorm_f32_to_f16(const float* x, const float* gamma, const float* beta, __half* y, int M, int D,
@@ -44,9 +52,6 @@ cudaError_t pool2_layernorm_f32(const float* x, const float* gamma, const float*
 // ---- attention (non-causal, no mask, Q pre-scaled): qkv f16 [B*T, 3*D] (q | k | v blocks of D = H*64), out f16 [B*T, D]
 // sched: two ints of device memory, zero before the first launch (the kernel leaves them zero again); one buffer per stream
 cudaError_t attention_f16_tcgen05(const __half* qkv, __half* out, int B, int T, int H, int* sched, cudaStream_t st);
-// round-1 bring-up kernel (mma.sync + cp.async): kept only as the "recompiled legacy tensor path" baseline the tests and
-// profiles compare against; the engine never calls it
-cudaError_t attention_f16(const __half* qkv, __half* out, int B, int T, int H, cudaStream_t st);
 
 // ---- mel front-end
 struct MelPlan;  // filterbank + tables resident on device

@@ -69,7 +69,7 @@ bool read_safe(whisper_model_loader* l, T& dst) {
 
 struct whisper_state {
     q2w_state* qs = nullptr;
-    int max_batch = 1;
+    bool owned = true;       // false: replica 0's state of a multi-device context (owned by the q2w_multi handle)
 };
 
 struct whisper_context {
@@ -80,11 +80,20 @@ struct whisper_context {
     int ftype = 1;           // hparams.ftype % factor
     int wtype = Q2W_TYPE_F16;
     int model_type = 0;      // e_model
-    q2w_model* model = nullptr;
+    q2w_model* model = nullptr;            // replica 0 (the only one unless gpu_device == -1 / an explicit device list)
+    std::vector<q2w_model*> replicas;      // one per device, replicas[0] == model
+    std::vector<int> devices;              // CUDA ordinals, parallel to replicas
+    q2w_multi* multi = nullptr;            // workers + states over all replicas (multi-device contexts only)
     whisper_state* state = nullptr;
     int max_batch = 16;
     std::string path_model;
 };
+
+static void free_models(whisper_context& c) {
+    for (q2w_model* m : c.replicas) q2w_model_free(m);
+    c.replicas.clear();
+    c.model = nullptr;
+}
 
 namespace {
 
@@ -93,6 +102,9 @@ bool model_load(whisper_model_loader* loader, whisper_context& wctx) {
     const int64_t t_start_us = now_us();
     wctx.t_start_us = t_start_us;
 
+    // every read is checked against the requested size: a file truncated anywhere -- inside the filterbank, a name, the last tensor's
+    // payload -- fails here instead of uploading stale bytes (the reference only notices a missing tensor, :1861)
+    auto read_exact = [&](void* dst, size_t n) { return n == 0 || loader->read(loader->context, dst, n) == n; };
     uint32_t magic = 0;
     read_safe(loader, magic);
     if (magic != FILE_MAGIC) {
@@ -134,42 +146,69 @@ bool model_load(whisper_model_loader* loader, whisper_context& wctx) {
 
     // mel filters (:1442-1451)
     int32_t n_mel = 0, n_fft = 0;
-    read_safe(loader, n_mel);
-    read_safe(loader, n_fft);
-    if (n_mel <= 0 || n_fft <= 0 || n_mel > 1024 || n_fft > 4096) {
+    if (!read_safe(loader, n_mel) || !read_safe(loader, n_fft) || n_mel <= 0 || n_fft <= 0 || n_mel > 1024 || n_fft > 4096) {
         LOG_ERROR("%s: invalid mel filterbank header (%d x %d)\n", "whisper_model_load", n_mel, n_fft);
         return false;
     }
     std::vector<float> filters(static_cast<size_t>(n_mel) * n_fft);
-    loader->read(loader->context, filters.data(), filters.size() * sizeof(float));
+    if (!read_exact(filters.data(), filters.size() * sizeof(float))) {
+        LOG_ERROR("%s: truncated model file (mel filterbank)\n", "whisper_model_load");
+        return false;
+    }
 
     // vocab (:1454-1487): parsed and dropped -- nothing on the encoder path reads it
     int32_t n_vocab = 0;
-    read_safe(loader, n_vocab);
+    if (!read_safe(loader, n_vocab) || n_vocab < 0) {
+        LOG_ERROR("%s: truncated model file (vocab header)\n", "whisper_model_load");
+        return false;
+    }
     std::vector<char> tmp;
     for (int i = 0; i < n_vocab; ++i) {
         uint32_t len = 0;
-        if (!read_safe(loader, len)) {
+        if (!read_safe(loader, len) || len > (1u << 20)) {
             LOG_ERROR("%s: truncated vocab\n", "whisper_model_load");
             return false;
         }
-        if (len > 0) {
-            tmp.resize(len);
-            loader->read(loader->context, tmp.data(), len);
+        tmp.resize(len);
+        if (!read_exact(tmp.data(), len)) {
+            LOG_ERROR("%s: truncated vocab\n", "whisper_model_load");
+            return false;
         }
     }
 
     hp.ftype = wctx.ftype;
-    int rc = q2w_model_create(&wctx.model, &hp, wctx.wtype, wctx.params.gpu_device);
-    if (rc != Q2W_OK) {
-        LOG_ERROR("%s: failed to allocate memory for the model: %s\n", "whisper_model_load", q2w_last_error());
-        return false;
+    // one weight replica per device: gpu_device >= 0 -> that device (the reference's meaning, include/qwen2-whisper.h:118);
+    // gpu_device == -1 -> every visible sm_100 device; an explicit list comes from whisper_init_*_multi
+    if (wctx.devices.empty()) {
+        if (wctx.params.gpu_device >= 0) {
+            wctx.devices.push_back(wctx.params.gpu_device);
+        } else {
+            const int n = q2w_device_count();
+            for (int d = 0; d < n; ++d) wctx.devices.push_back(d);
+            if (wctx.devices.empty()) {
+                LOG_ERROR("%s: gpu_device = -1 but no sm_100 device is visible\n", "whisper_model_load");
+                return false;
+            }
+        }
     }
-    LOG_INFO("%s: %8s total size = %8.2f MB\n", "whisper_model_load", "CUDA0", q2w_model_weight_bytes(wctx.model) / 1e6);
-    if ((rc = q2w_model_upload_filters(wctx.model, filters.data(), n_mel, n_fft)) != Q2W_OK) {
-        LOG_ERROR("%s: %s\n", "whisper_model_load", q2w_last_error());
-        return false;
+    int rc = Q2W_OK;
+    for (size_t r = 0; r < wctx.devices.size(); ++r) {
+        q2w_model* m = nullptr;
+        rc = q2w_model_create(&m, &hp, wctx.wtype, wctx.devices[r]);
+        if (rc != Q2W_OK) {
+            LOG_ERROR("%s: failed to allocate memory for the model on device %d: %s\n", "whisper_model_load", wctx.devices[r], q2w_last_error());
+            return false;
+        }
+        wctx.replicas.push_back(m);
+        char nm[16];
+        snprintf(nm, sizeof(nm), "CUDA%d", wctx.devices[r]);
+        LOG_INFO("%s: %8s total size = %8.2f MB\n", "whisper_model_load", nm, q2w_model_weight_bytes(m) / 1e6);
+        if ((rc = q2w_model_upload_filters(m, filters.data(), n_mel, n_fft)) != Q2W_OK) {
+            LOG_ERROR("%s: %s\n", "whisper_model_load", q2w_last_error());
+            return false;
+        }
     }
+    wctx.model = wctx.replicas[0];
 
     // tensor stream (:1782-1855)
     size_t total_size = 0;
@@ -177,42 +216,56 @@ bool model_load(whisper_model_loader* loader, whisper_context& wctx) {
     std::vector<char> read_buf;
     while (true) {
         int32_t n_dims = 0, length = 0, ttype = 0;
-        read_safe(loader, n_dims);
-        read_safe(loader, length);
-        read_safe(loader, ttype);
-        if (loader->eof(loader->context)) break;
+        const bool got_dims = read_safe(loader, n_dims);
+        if (!got_dims && loader->eof(loader->context)) break;          // clean end of the tensor stream (:1787-1790)
+        if (!got_dims || !read_safe(loader, length) || !read_safe(loader, ttype)) {
+            LOG_ERROR("%s: truncated model file (tensor header)\n", "whisper_model_load");
+            return false;
+        }
         if (n_dims < 1 || n_dims > 4 || length < 0 || length > 4096) {
             LOG_ERROR("%s: corrupt tensor record (n_dims %d, name length %d)\n", "whisper_model_load", n_dims, length);
             return false;
         }
-        int32_t nelements = 1;
+        int64_t nelements = 1;
         int32_t ne[4] = {1, 1, 1, 1};
         for (int i = 0; i < n_dims; ++i) {
-            read_safe(loader, ne[i]);
-            nelements *= ne[i];
+            if (!read_safe(loader, ne[i]) || ne[i] <= 0 || (nelements *= ne[i]) > (int64_t(1) << 40)) {
+                LOG_ERROR("%s: truncated or corrupt tensor record (dims)\n", "whisper_model_load");
+                return false;
+            }
         }
         std::string name(static_cast<size_t>(length), '\0');
-        loader->read(loader->context, &name[0], name.size());
+        if (!read_exact(&name[0], name.size())) {
+            LOG_ERROR("%s: truncated model file (tensor name)\n", "whisper_model_load");
+            return false;
+        }
         const size_t bpe = type_size(ttype);
-        if (bpe == 0 || nelements <= 0 || ne[0] % blck_size(ttype)) {
+        if (bpe == 0 || ne[0] % blck_size(ttype)) {
             LOG_ERROR("%s: tensor '%s' has unsupported type %d or bad shape\n", "whisper_model_load", name.c_str(), ttype);
             return false;
         }
         const size_t nbytes = static_cast<size_t>(nelements) / blck_size(ttype) * bpe;
         read_buf.resize(nbytes);
-        loader->read(loader->context, read_buf.data(), nbytes);
-        rc = q2w_model_upload_tensor(wctx.model, name.c_str(), ttype, std::min(n_dims, 3), ne, read_buf.data(), nbytes);
-        if (rc != Q2W_OK) {
-            LOG_ERROR("%s: %s\n", "whisper_model_load", q2w_last_error());
+        if (!read_exact(read_buf.data(), nbytes)) {
+            LOG_ERROR("%s: truncated model file: tensor '%s' needs %zu bytes\n", "whisper_model_load", name.c_str(), nbytes);
             return false;
+        }
+        for (q2w_model* m : wctx.replicas) {
+            rc = q2w_model_upload_tensor(m, name.c_str(), ttype, std::min(n_dims, 3), ne, read_buf.data(), nbytes);
+            if (rc != Q2W_OK) {
+                LOG_ERROR("%s: %s\n", "whisper_model_load", q2w_last_error());
+                return false;
+            }
         }
         total_size += nbytes;
         n_loaded++;
     }
     LOG_INFO("%s: model size    = %7.2f MB\n", "whisper_model_load", total_size / 1e6);
-    if ((rc = q2w_model_finalize(wctx.model)) != Q2W_OK) {
-        LOG_ERROR("%s: ERROR %s\n", "whisper_model_load", q2w_last_error());
-        return false;
+    for (q2w_model* m : wctx.replicas) {
+        if ((rc = q2w_model_finalize(m)) != Q2W_OK) {
+            LOG_ERROR("%s: ERROR %s\n", "whisper_model_load", q2w_last_error());
+            return false;
+        }
     }
     (void) n_loaded;
     wctx.t_load_us = now_us() - t_start_us;
@@ -272,7 +325,7 @@ struct whisper_full_params* whisper_full_default_params_by_ref(void) {
 void whisper_free_context_params(struct whisper_context_params* params) { delete params; }
 void whisper_free_params(struct whisper_full_params* params) { delete params; }
 
-struct whisper_context* whisper_init_with_params_no_state(struct whisper_model_loader* loader, struct whisper_context_params params) {
+static whisper_context* init_no_state(struct whisper_model_loader* loader, struct whisper_context_params params, const int* devices, int n_devices) {
     if (!loader || !loader->read || !loader->eof || !loader->close) {
         LOG_ERROR("%s: invalid model loader\n", __func__);
         return nullptr;
@@ -292,10 +345,11 @@ struct whisper_context* whisper_init_with_params_no_state(struct whisper_model_l
     }
     whisper_context* ctx = new whisper_context;
     ctx->params = params;
+    for (int i = 0; i < n_devices; ++i) ctx->devices.push_back(devices[i]);
     if (!model_load(loader, *ctx)) {
         loader->close(loader->context);
         LOG_ERROR("%s: failed to load model\n", __func__);
-        if (ctx->model) q2w_model_free(ctx->model);
+        free_models(*ctx);
         delete ctx;
         return nullptr;
     }
@@ -303,16 +357,16 @@ struct whisper_context* whisper_init_with_params_no_state(struct whisper_model_l
     return ctx;
 }
 
-struct whisper_context* whisper_init_from_file_with_params_no_state(const char* path_model, struct whisper_context_params params) {
-    LOG_INFO("%s: loading model from '%s'\n", __func__, path_model ? path_model : "(null)");
-    std::ifstream fin;
-    if (path_model) fin.open(path_model, std::ios::binary);
-    if (!path_model || !fin) {
-        LOG_ERROR("%s: failed to open '%s'\n", __func__, path_model ? path_model : "(null)");
-        return nullptr;
-    }
+struct whisper_context* whisper_init_with_params_no_state(struct whisper_model_loader* loader, struct whisper_context_params params) {
+    return init_no_state(loader, params, nullptr, 0);
+}
+
+namespace {
+// std::ifstream / memory-buffer loaders shared by the _from_file / _from_buffer entry points
+struct buf_context { uint8_t* p; size_t size; size_t off; bool hit_end; };
+whisper_model_loader file_loader(std::ifstream* fin) {
     whisper_model_loader loader = {};
-    loader.context = &fin;
+    loader.context = fin;
     loader.read = [](void* c, void* out, size_t n) -> size_t {
         std::ifstream* f = static_cast<std::ifstream*>(c);
         f->read(static_cast<char*>(out), static_cast<std::streamsize>(n));
@@ -320,21 +374,11 @@ struct whisper_context* whisper_init_from_file_with_params_no_state(const char* 
     };
     loader.eof = [](void* c) -> bool { return static_cast<std::ifstream*>(c)->eof(); };
     loader.close = [](void* c) { static_cast<std::ifstream*>(c)->close(); };
-    whisper_context* ctx = whisper_init_with_params_no_state(&loader, params);
-    if (ctx) ctx->path_model = path_model;
-    return ctx;
+    return loader;
 }
-
-struct whisper_context* whisper_init_from_buffer_with_params_no_state(void* buffer, size_t buffer_size, struct whisper_context_params params) {
-    struct buf_context { uint8_t* p; size_t size; size_t off; bool hit_end; };
-    buf_context bc = {static_cast<uint8_t*>(buffer), buffer_size, 0, false};
-    LOG_INFO("%s: loading model from buffer\n", __func__);
-    if (!buffer) {
-        LOG_ERROR("%s: null buffer\n", __func__);
-        return nullptr;
-    }
+whisper_model_loader buffer_loader(buf_context* bc) {
     whisper_model_loader loader = {};
-    loader.context = &bc;
+    loader.context = bc;
     loader.read = [](void* c, void* out, size_t n) -> size_t {
         buf_context* b = static_cast<buf_context*>(c);
         const size_t k = std::min(n, b->size - b->off);
@@ -346,14 +390,49 @@ struct whisper_context* whisper_init_from_buffer_with_params_no_state(void* buff
     // like an ifstream, eof only turns true once a read ran past the end (so a file ending exactly after a tensor works)
     loader.eof = [](void* c) -> bool { return static_cast<buf_context*>(c)->hit_end; };
     loader.close = [](void*) {};
-    return whisper_init_with_params_no_state(&loader, params);
+    return loader;
+}
+}  // namespace
+
+static whisper_context* init_from_file_no_state(const char* path_model, struct whisper_context_params params, const int* devices, int n_devices,
+                                                const char* fn) {
+    LOG_INFO("%s: loading model from '%s'\n", fn, path_model ? path_model : "(null)");
+    std::ifstream fin;
+    if (path_model) fin.open(path_model, std::ios::binary);
+    if (!path_model || !fin) {
+        LOG_ERROR("%s: failed to open '%s'\n", fn, path_model ? path_model : "(null)");
+        return nullptr;
+    }
+    whisper_model_loader loader = file_loader(&fin);
+    whisper_context* ctx = init_no_state(&loader, params, devices, n_devices);
+    if (ctx) ctx->path_model = path_model;
+    return ctx;
+}
+
+static whisper_context* init_from_buffer_no_state(void* buffer, size_t buffer_size, struct whisper_context_params params, const int* devices,
+                                                  int n_devices, const char* fn) {
+    LOG_INFO("%s: loading model from buffer\n", fn);
+    if (!buffer) {
+        LOG_ERROR("%s: null buffer\n", fn);
+        return nullptr;
+    }
+    buf_context bc = {static_cast<uint8_t*>(buffer), buffer_size, 0, false};
+    whisper_model_loader loader = buffer_loader(&bc);
+    return init_no_state(&loader, params, devices, n_devices);
+}
+
+struct whisper_context* whisper_init_from_file_with_params_no_state(const char* path_model, struct whisper_context_params params) {
+    return init_from_file_no_state(path_model, params, nullptr, 0, __func__);
+}
+
+struct whisper_context* whisper_init_from_buffer_with_params_no_state(void* buffer, size_t buffer_size, struct whisper_context_params params) {
+    return init_from_buffer_no_state(buffer, buffer_size, params, nullptr, 0, __func__);
 }
 
 struct whisper_state* whisper_init_state(struct whisper_context* ctx) {
     if (!ctx || !ctx->model) return nullptr;
     whisper_state* st = new whisper_state;
-    st->max_batch = ctx->max_batch;
-    const int rc = q2w_state_create(&st->qs, ctx->model, st->max_batch);
+    const int rc = q2w_state_create(&st->qs, ctx->model, ctx->max_batch);
     if (rc != Q2W_OK) {
         LOG_ERROR("%s: whisper_backend_init() failed: %s\n", __func__, q2w_last_error());
         delete st;
@@ -362,8 +441,22 @@ struct whisper_state* whisper_init_state(struct whisper_context* ctx) {
     return st;
 }
 
+// default state. One device: a plain state. Several replicas: the multi-device handle owns one state per replica (plus one host
+// worker thread each) and the context's default state is replica 0's, so the single-window API keeps working unchanged.
 static whisper_context* with_state(whisper_context* ctx) {
     if (!ctx) return nullptr;
+    if (ctx->replicas.size() > 1) {
+        const int rc = q2w_multi_create(&ctx->multi, ctx->replicas.data(), static_cast<int>(ctx->replicas.size()), ctx->max_batch);
+        if (rc != Q2W_OK) {
+            LOG_ERROR("%s: multi-device init failed: %s\n", __func__, q2w_last_error());
+            whisper_free(ctx);
+            return nullptr;
+        }
+        ctx->state = new whisper_state;
+        ctx->state->qs = q2w_multi_state(ctx->multi, 0);
+        ctx->state->owned = false;
+        return ctx;
+    }
     ctx->state = whisper_init_state(ctx);
     if (!ctx->state) {
         whisper_free(ctx);
@@ -382,16 +475,48 @@ struct whisper_context* whisper_init_with_params(struct whisper_model_loader* lo
     return with_state(whisper_init_with_params_no_state(loader, params));
 }
 
+// the deprecated spellings (src/qwen2-whisper.cpp:3184-3206): default params
+struct whisper_context* whisper_init_from_file(const char* path_model) {
+    return whisper_init_from_file_with_params(path_model, whisper_context_default_params());
+}
+struct whisper_context* whisper_init_from_buffer(void* buffer, size_t buffer_size) {
+    return whisper_init_from_buffer_with_params(buffer, buffer_size, whisper_context_default_params());
+}
+struct whisper_context* whisper_init(struct whisper_model_loader* loader) {
+    return whisper_init_with_params(loader, whisper_context_default_params());
+}
+struct whisper_context* whisper_init_from_file_no_state(const char* path_model) {
+    return whisper_init_from_file_with_params_no_state(path_model, whisper_context_default_params());
+}
+struct whisper_context* whisper_init_from_buffer_no_state(void* buffer, size_t buffer_size) {
+    return whisper_init_from_buffer_with_params_no_state(buffer, buffer_size, whisper_context_default_params());
+}
+struct whisper_context* whisper_init_no_state(struct whisper_model_loader* loader) {
+    return whisper_init_with_params_no_state(loader, whisper_context_default_params());
+}
+
+// additive: an explicit device list (one weight replica per entry; the same ordinal may appear more than once)
+struct whisper_context* whisper_init_from_file_multi(const char* path_model, struct whisper_context_params params, const int* devices, int n_devices) {
+    if (!devices || n_devices < 1) return nullptr;
+    return with_state(init_from_file_no_state(path_model, params, devices, n_devices, __func__));
+}
+struct whisper_context* whisper_init_from_buffer_multi(void* buffer, size_t buffer_size, struct whisper_context_params params, const int* devices,
+                                                       int n_devices) {
+    if (!devices || n_devices < 1) return nullptr;
+    return with_state(init_from_buffer_no_state(buffer, buffer_size, params, devices, n_devices, __func__));
+}
+
 void whisper_free_state(struct whisper_state* state) {
     if (!state) return;
-    q2w_state_free(state->qs);
+    if (state->owned) q2w_state_free(state->qs);
     delete state;
 }
 
 void whisper_free(struct whisper_context* ctx) {
     if (!ctx) return;
     whisper_free_state(ctx->state);
-    if (ctx->model) q2w_model_free(ctx->model);
+    if (ctx->multi) q2w_multi_free(ctx->multi);
+    free_models(*ctx);
     delete ctx;
 }
 
@@ -566,19 +691,47 @@ int whisper_get_mel_dims(struct whisper_context* ctx, int* n_len, int* n_len_org
     if (n_mel) *n_mel = ctx->hp.n_mels;
     return 0;
 }
+// windows per micro-batch (per device). The default state's scratch is resized in place: its mel and embeddings survive.
 int whisper_set_max_batch(struct whisper_context* ctx, int max_batch) {
     if (!ctx || max_batch < 1) return -1;
-    if (ctx->state && ctx->state->max_batch == max_batch) return 0;
-    ctx->max_batch = max_batch;
-    if (ctx->state) {
-        whisper_free_state(ctx->state);
-        ctx->state = whisper_init_state(ctx);
-        if (!ctx->state) return -1;
+    ctx->max_batch = max_batch;            // states created from now on (whisper_init_state) use it too
+    int rc = Q2W_OK;
+    if (ctx->multi) rc = q2w_multi_set_max_batch(ctx->multi, max_batch);
+    else if (ctx->state) rc = q2w_state_set_max_batch(ctx->state->qs, max_batch);
+    if (rc != Q2W_OK) {
+        LOG_ERROR("%s: %s\n", __func__, q2w_last_error());
+        return -1;
     }
     return 0;
 }
+int whisper_n_devices(struct whisper_context* ctx) { return ctx ? static_cast<int>(ctx->replicas.size()) : 0; }
+int whisper_device(struct whisper_context* ctx, int i) { return (ctx && i >= 0 && i < static_cast<int>(ctx->devices.size())) ? ctx->devices[i] : -1; }
+// all devices of the context: window w -> device floor(w * G / n_windows), results in caller order in dst (if non-NULL);
+// gather_device >= 0 also assembles every embedding on that device (whisper_get_gathered_device). One device: == whisper_encode_batch.
+int whisper_encode_batch_multi(struct whisper_context* ctx, const float* samples, size_t stride, const int32_t* n_samples, int n_windows, float* dst,
+                               int gather_device) {
+    if (!ctx || !ctx->state) return -1;
+    if (!ctx->multi) {
+        if (gather_device >= 0 && gather_device != ctx->devices[0]) {
+            LOG_ERROR("%s: gather device %d is not a device of this context\n", __func__, gather_device);
+            return -1;
+        }
+        return whisper_encode_batch(ctx, samples, stride, n_samples, n_windows, dst);
+    }
+    if (q2w_multi_encode_batch_host(ctx->multi, samples, stride, n_samples, n_windows, dst, gather_device) != Q2W_OK) {
+        LOG_ERROR("%s: failed to encode: %s\n", __func__, q2w_last_error());
+        return -1;
+    }
+    return 0;
+}
+const float* whisper_get_gathered_device(struct whisper_context* ctx) {
+    if (!ctx) return nullptr;
+    return ctx->multi ? q2w_multi_gathered_device(ctx->multi) : (ctx->state ? q2w_embeddings_device(ctx->state->qs) : nullptr);
+}
+void* whisper_q2w_multi(struct whisper_context* ctx) { return ctx ? ctx->multi : nullptr; }
 int whisper_encode_batch(struct whisper_context* ctx, const float* samples, size_t stride, const int32_t* n_samples, int n_windows, float* dst) {
     if (!ctx || !ctx->state) return -1;
+    if (ctx->multi) return whisper_encode_batch_multi(ctx, samples, stride, n_samples, n_windows, dst, -1);
     if (q2w_encode_batch_host(ctx->state->qs, samples, stride, n_samples, n_windows, dst) != Q2W_OK) {
         LOG_ERROR("%s: failed to encode: %s\n", __func__, q2w_last_error());
         return -1;

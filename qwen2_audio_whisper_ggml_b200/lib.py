@@ -71,7 +71,24 @@ _SIGS = {
     "q2w_op_layernorm": (_i, [_vp, _vp, _vp, _vp, _i, _i, _f, _vp]),
     "q2w_op_pool_layernorm": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp]),
     "q2w_op_attention": (_i, [_vp, _vp, _i, _i, _i, _vp]),
-    "q2w_op_attention_legacy_mma": (_i, [_vp, _vp, _i, _i, _i, _vp]),
+    "q2w_op_conv1_operand": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _i, _i, _vp, _vp]),
+    "q2w_op_set_gemm_splitk": (None, [_i]),
+    "q2w_debug_forward_layers": (_i, [_vp, _i]),
+    "q2w_debug_get_residual": (_i, [_vp, _i, _vp]),
+    "q2w_model_device": (_i, [_vp]),
+    "q2w_multi_create": (_i, [C.POINTER(_vp), C.POINTER(_vp), _i, _i]),
+    "q2w_multi_free": (None, [_vp]),
+    "q2w_multi_n_devices": (_i, [_vp]),
+    "q2w_multi_device": (_i, [_vp, _i]),
+    "q2w_multi_state": (_vp, [_vp, _i]),
+    "q2w_multi_shard_bounds": (_i, [_vp, _i, _i, C.POINTER(_i), C.POINTER(_i)]),
+    "q2w_multi_set_max_batch": (_i, [_vp, _i]),
+    "q2w_multi_encode_batch_host": (_i, [_vp, _vp, _sz, _vp, _i, _vp, _i]),
+    "q2w_multi_gathered_device": (_vp, [_vp]),
+    "q2w_multi_get_gathered": (_i, [_vp, _vp, _sz]),
+    "q2w_multi_last_device_ms": (C.c_double, [_vp, _i]),
+    "q2w_state_set_max_batch": (_i, [_vp, _i]),
+    "q2w_state_max_batch": (_i, [_vp]),
     "q2w_op_dequant": (_i, [_vp, _i, _vp, _sz, _i, _vp]),
     "q2w_op_conv2_im2col": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "q2w_op_mel": (_i, [_vp, _i, _vp, _sz, _vp, _i, _i, _i, _vp, _i, _vp, _i, _vp]),

@@ -64,9 +64,48 @@ def test_gemm(lib, M, N, K, epi):
     assert rel_l2(got, want) < tol, (rel_l2(got, want), max_abs(got, want))
 
 
+@pytest.fixture
+def single_pass_gemm(lib):
+    """pin the bit-reproducible single-pass residual epilogue (no split-K) for tests that compare outputs bit for bit"""
+    lib.q2w_op_set_gemm_splitk(0)
+    yield
+    lib.q2w_op_set_gemm_splitk(-1)
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("M,N,K", [(1500, 1280, 1280), (1500, 1280, 5120), (700, 1280, 5120), (257, 256, 2048), (100, 1280, 5120), (1500, 1288, 1096)])
+def test_gemm_residual_split_k(lib, mode, M, N, K):
+    """small-M residual epilogue with the K range cut over several CTA pairs (each partial is a TMA reduction store into x, the
+    bias rides on the segment that holds k-block 0): same answer as the single pass up to the order of the F32 adds, on top of a
+    NaN-free residual; rows >= M / columns >= N of a wider buffer stay untouched"""
+    g = torch.Generator(device="cuda").manual_seed(M + N + K + mode)
+    A = (torch.randn(M, K, device="cuda", generator=g) * 0.5).half()
+    W = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).half()
+    bias = torch.randn(N, device="cuda", generator=g) * 0.1
+    resid = torch.randn(M + 3, N + 8, device="cuda", generator=g)
+    want = resid.clone()
+    want[:M, :N] += A.float() @ W.float().t() + bias
+    outs = []
+    try:
+        for md in (0, mode, mode):
+            lib.q2w_op_set_gemm_splitk(md)
+            out = resid.clone()
+            ck(lib.q2w_op_gemm(A.data_ptr(), K, W.data_ptr(), K, M, N, K, bias.data_ptr(), out.data_ptr(), N + 8, L.EPI_BIAS_RESID_F32,
+                               out.data_ptr(), None, 0, 0, 1.0, None))
+            outs.append(out)
+    finally:
+        lib.q2w_op_set_gemm_splitk(-1)
+    for out in outs:
+        assert torch.equal(out[M:], resid[M:]) and torch.equal(out[:, N:], resid[:, N:])
+        assert rel_l2(out.cpu().numpy(), want.cpu().numpy()) < 2e-5
+    # split and single pass agree to F32 rounding of a handful of adds (not bit for bit: the L2 adds arrive in any order)
+    assert max_abs(outs[1].cpu().numpy(), outs[0].cpu().numpy()) < 2e-5
+    assert max_abs(outs[2].cpu().numpy(), outs[1].cpu().numpy()) < 2e-5
+
+
 @pytest.mark.parametrize("ttype", [gq.GGML_TYPE_Q8_0, gq.GGML_TYPE_Q4_0])
 @pytest.mark.parametrize("M,N,K,epi", [(300, 384, 128, 0), (1500, 1280, 1280, 2), (2100, 5120, 1280, 1), (777, 1280, 5120, 2), (520, 136, 192, 4)])
-def test_gemm_in_kernel_dequant(lib, ttype, M, N, K, epi):
+def test_gemm_in_kernel_dequant(lib, single_pass_gemm, ttype, M, N, K, epi):
     """W stays in ggml blocks; the GEMM's decode warpgroup must reproduce dequantize_row_* + F16 rounding exactly, so the result
     equals the F16-weight GEMM on the decoded matrix bit for bit"""
     rng = np.random.default_rng(M + N + K + ttype)
@@ -186,6 +225,48 @@ def test_dequant_bit_exact(lib, ttype):
     dst = torch.empty(rows, K, device="cuda", dtype=torch.half)
     ck(lib.q2w_op_dequant(src.data_ptr(), ttype, dst.data_ptr(), rows, K, None))
     assert np.array_equal(dst.cpu().numpy().view(np.uint16), want.view(np.uint16))
+
+
+@pytest.mark.parametrize("ttype", [gq.GGML_TYPE_Q8_0, gq.GGML_TYPE_Q4_0])
+def test_gemm_in_kernel_dequant_split_k(lib, ttype):
+    """the decode warpgroup follows the same (tile, k-range) segments as the producer when the K range is cut"""
+    M, N, K = 1500, 1280, 5120
+    rng = np.random.default_rng(ttype)
+    w = (rng.standard_normal((N, K)) / K ** 0.5).astype(np.float32)
+    raw = gq.quantize(w, ttype).reshape(-1)
+    wdq = torch.from_numpy(gq.dequantize(raw, ttype, K).astype(np.float16)).cuda()
+    g = torch.Generator(device="cuda").manual_seed(4)
+    A = (torch.randn(M, K, device="cuda", generator=g) * 0.5).half()
+    bias = torch.randn(N, device="cuda", generator=g) * 0.1
+    resid = torch.randn(M, N, device="cuda", generator=g)
+    d_raw = torch.from_numpy(raw.copy()).cuda()
+    out = resid.clone()
+    ck(lib.q2w_op_gemm_q(A.data_ptr(), K, d_raw.data_ptr(), ttype, M, N, K, bias.data_ptr(), out.data_ptr(), N, 2, out.data_ptr(), 0, 1.0, None))
+    want = resid + A.float() @ wdq.float().t() + bias
+    assert rel_l2(out.cpu().numpy(), want.cpu().numpy()) < 2e-5
+
+
+@pytest.mark.parametrize("offset,n_valid,normalise", [(0, 6000, 1), (2900, 3100, 1), (17, 230, 0), (5990, 6000, 1), (6000, 6000, 0)])
+def test_conv1_operand(lib, offset, n_valid, normalise):
+    """window slice [offset, offset + 2 n_ctx) + zero fill past n_len (src/qwen2-whisper.cpp:2274-2283) + max(x, max - 8), (x + 4) / 4
+    (:2643-2649, fused here) + im2col k3 s1 p1 in ggml column order ic * 3 + k, for two windows with different maxima"""
+    B, n_mel, n_ctx2, ld = 2, 128, 3000, 6016
+    g = torch.Generator(device="cuda").manual_seed(offset + n_valid)
+    mel = torch.randn(B, n_mel, ld, device="cuda", generator=g) * 2.0 - 3.0
+    mx = mel[:, :, :n_valid].amax(dim=(1, 2))
+    bits = mx.view(torch.int32)
+    keys = torch.where(bits >= 0, bits, bits ^ 0x7FFFFFFF).contiguous()                 # order-preserving int key (mel.cu float_to_key)
+    A1 = torch.full((B * n_ctx2, 3 * n_mel), float("nan"), device="cuda", dtype=torch.half)
+    ck(lib.q2w_op_conv1_operand(mel.data_ptr(), ld, n_valid, n_mel, keys.data_ptr(), normalise, offset, n_ctx2, B, A1.data_ptr(), None))
+    win = torch.zeros(B, n_mel, n_ctx2 + 2, device="cuda")                               # one zero column of conv padding either side
+    n_take = max(0, min(n_ctx2, n_valid - offset))
+    src = mel[:, :, offset:offset + n_take]
+    if normalise:
+        src = (torch.maximum(src, (mx - 8.0).view(B, 1, 1)) + 4.0) / 4.0
+    win[:, :, 1:1 + n_take] = src
+    cols = torch.stack([win[:, :, k:k + n_ctx2] for k in range(3)], dim=-1)              # [B, n_mel, n_ctx2, 3]
+    want = cols.permute(0, 2, 1, 3).reshape(B * n_ctx2, 3 * n_mel).half()
+    assert torch.equal(A1, want)
 
 
 def test_conv2_im2col(lib):

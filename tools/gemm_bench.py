@@ -36,7 +36,7 @@ for name, m, n, k, epi in shapes:
 H, T = 20, 1500
 qkv = (torch.randn(B * T, 3 * H * 64, device="cuda", generator=g) * 0.5).half()
 o = torch.empty(B * T, H * 64, device="cuda", dtype=torch.half)
-for nm, fn in (("attention tcgen05", lib.q2w_op_attention), ("attention legacy mma.sync", lib.q2w_op_attention_legacy_mma)):
+for nm, fn in (("attention tcgen05", lib.q2w_op_attention),):
     for _ in range(2):
         L.check(fn(qkv.data_ptr(), o.data_ptr(), B, T, H, None))
     torch.cuda.synchronize()
