@@ -110,15 +110,18 @@ class EncoderOracle:
         h = gelu_tanh(conv(h, self.w["conv2.weight"], self.w["conv2.bias"], 2), via)
         return np.ascontiguousarray(h.T)
 
-    def encode(self, mel_win: np.ndarray, return_pre_pool: bool = False, n_layers: int | None = None) -> np.ndarray:
+    def encode(self, mel_win: np.ndarray, return_pre_pool: bool = False, n_layers: int | None = None, taps: dict | None = None) -> np.ndarray:
         """n_layers: stop after that many encoder blocks (0 = conv stem + positional embedding); with return_pre_pool the residual
-        stream at that point comes back -- `cur` / `inpL` of whisper_build_graph_encoder (:2005, :2154) -- for the stage tests"""
+        stream at that point comes back -- `cur` / `inpL` of whisper_build_graph_encoder (:2005, :2154) -- for the stage tests.
+        taps: a dict whose keys are layer counts; each is filled with a copy of the residual stream after that many blocks"""
         hp = self.hp
         T, D, H, L = hp["n_audio_ctx"], hp["n_audio_state"], hp["n_audio_head"], hp["n_audio_layer"]
         hd = D // H
         via = self.mode == "ggml"
         x = self.conv_stem(mel_win) + self.w["embed_positions.weight"][:T]
         scale = np.float32(1.0 / np.sqrt(float(hd)))
+        if taps is not None and 0 in taps:
+            taps[0] = x.copy()
         for i in range(L if n_layers is None else min(L, n_layers)):
             p = f"layers.{i}."
             c = layer_norm(x, self.w[p + "self_attn_layer_norm.weight"], self.w[p + "self_attn_layer_norm.bias"])
@@ -137,6 +140,8 @@ class EncoderOracle:
             c = layer_norm(x, self.w[p + "final_layer_norm.weight"], self.w[p + "final_layer_norm.bias"])
             hmid = gelu_tanh(self._matmul(c, p + "fc1.weight") + self.w[p + "fc1.bias"], via)
             x = x + self._matmul(hmid, p + "fc2.weight") + self.w[p + "fc2.bias"]
+            if taps is not None and (i + 1) in taps:
+                taps[i + 1] = x.copy()
         if return_pre_pool:
             return x
         y = ((x[0::2] + x[1::2]) / np.float32(2.0)).astype(np.float32)      # ggml_pool_1d AVG k2 s2 (:2165)

@@ -1059,6 +1059,8 @@ int q2w_op_gemm(const void* A, int lda, const void* W, int ldw, int M, int N, in
     g.A = static_cast<const __half*>(A); g.lda = lda; g.W = static_cast<const __half*>(W); g.ldw = ldw;
     g.M = M; g.N = N; g.K = K; g.bias = bias; g.out = out; g.ldo = ldo; g.resid = resid; g.pos = pos; g.pos_period = pos_period;
     g.scale_cols = scale_cols; g.scale = scale;
+    static const int w_static = [] { const char* e = getenv("Q2W_OP_W_STATIC"); return e ? atoi(e) : 0; }();   // tools/gemm_b1.py: W is a constant there
+    g.w_static = w_static;
     CKL(gemm_f16_tcgen05(g, static_cast<GemmEpilogue>(epilogue), static_cast<cudaStream_t>(stream)));
     return Q2W_OK;
 }

@@ -175,6 +175,18 @@ __device__ __forceinline__ void decode_row(const uint32_t (&w)[DqTraits<WT>::WOR
     }
 }
 
+#ifdef Q2W_GEMM_WALL
+// wall-clock stamps (make EXTRA_NVFLAGS=-DQ2W_GEMM_WALL, tools/gemm_wall.py): where a small-M launch spends its time
+__device__ __forceinline__ unsigned long long gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define WALL(var) const unsigned long long var = gtime()
+#else
+#define WALL(var)
+#endif
+
 template <int EPI, int WT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WT == WT_F16 ? NUM_THREADS : NUM_THREADS_Q, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -199,6 +211,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int cluster_id = blockIdx.x >> 1;
     const int num_clusters = gridDim.x >> 1;
     const int nkb = (p.K + BK - 1) / BK;
+    WALL(w_entry);
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
@@ -239,8 +252,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
         }
     }
+    WALL(w_prolog);
     pdl_wait();                  // everything above overlapped the previous kernel's tail; from here on its output is visible
     pdl_launch_dependents();
+    WALL(w_wait);
 
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer (both CTAs)
@@ -283,6 +298,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             int my_tiles = 0;
             const long long t_begin = clock64();
 #endif
+#ifdef Q2W_GEMM_WALL
+            unsigned long long w_first = 0;
+#endif
             WorkIter wi(p, nkb, cluster_id, num_clusters);
             int tile, kb0, kb1;
             while (wi.next(tile, kb0, kb1)) {
@@ -302,6 +320,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #endif
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
+#ifdef Q2W_GEMM_WALL
+                    if (w_first == 0) w_first = gtime();
+#endif
 #ifdef Q2W_GEMM_TIMELINE
                     { const long long dt = clock64() - w0; t_full += dt; if (dt > 200) ++n_slow; }
 #endif
@@ -318,6 +339,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1;
             }
+#ifdef Q2W_GEMM_WALL
+            if (cluster_id == 0 || cluster_id == num_clusters - 1)
+                printf("GW mma c%d/%d N%d K%d entry %llu prolog %llu wait %llu first_operands %llu issued_all %llu\n", cluster_id, num_clusters, p.N, p.K, w_entry,
+                       w_prolog, w_wait, w_first, gtime());
+#endif
 #ifdef Q2W_GEMM_TIMELINE
             if (cluster_id == 3 && my_tiles > 0) {
                 const long long tot = clock64() - t_begin;
@@ -388,14 +414,25 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         long gc = 0;                               // running chunk counter: buffer rotation
         int acc = 0;
         uint32_t acc_phase = 0;
+#ifdef Q2W_GEMM_WALL
+        unsigned long long w_acc = 0;
+#endif
         WorkIter wi(p, nkb, cluster_id, num_clusters);
         int tile, kb0, kb1;
         while (wi.next(tile, kb0, kb1)) {
             const int m0 = (tile / p.n_tiles) * (2 * BM) + static_cast<int>(cta_rank) * BM + q * 32;
             const int nbase = (tile % p.n_tiles) * BN + chalf * (BN / 2);
             const bool add_bias = p.bias != nullptr && kb0 == 0;   // split-K: only the segment that starts the K range carries the bias
+            // this warp's 128 bias values, four per lane, requested BEFORE the accumulator wait and handed out by shuffles below: a
+            // per-chunk global load put one L2 / HBM round trip per chunk on the critical path of a single-tile launch (measured
+            // 4-5 us between "accumulator ready" and "last store issued" at M = 1500)
+            float4 breg = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (add_bias && nbase + 4 * lane < p.N) breg = __ldg(reinterpret_cast<const float4*>(p.bias + nbase + 4 * lane));
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
+#ifdef Q2W_GEMM_WALL
+            w_acc = gtime();
+#endif
             const uint32_t t_row = tmem_base + acc * BN + chalf * (BN / 2) + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll 1
             for (int c = 0; c < CHUNKS; ++c, ++gc) {
@@ -403,6 +440,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 const int b = static_cast<int>(gc % EPI_BUFS);
                 uint8_t* buf = bufs + b * CHUNK_BYTES;
                 float v[CCOLS];
+#ifdef Q2W_GEMM_WALL
+                const unsigned long long wc0 = gtime();
+#endif
                 {
                     uint32_t r[32];
                     tmem_ld_32x32b_x32(t_row + c * CCOLS, r);
@@ -425,13 +465,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     if (lane == 0) mbar_arrive_cluster(&tempty_bar[acc], 0);
                 }
                 // ---- bias (+ scale / GELU / positional) in registers; the column index is uniform across the warp
-                if (add_bias) {
+                if (add_bias) {                                    // warp-uniform
 #pragma unroll
                     for (int g = 0; g < CCOLS / 4; ++g) {
-                        if (n + 4 * g < p.N) {
-                            const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4 * g));
-                            v[4 * g + 0] += bv.x; v[4 * g + 1] += bv.y; v[4 * g + 2] += bv.z; v[4 * g + 3] += bv.w;
-                        }
+                        const int src = c * (CCOLS / 4) + g;           // lane that holds columns [n + 4g, n + 4g + 4)
+                        v[4 * g + 0] += __shfl_sync(0xffffffffu, breg.x, src);
+                        v[4 * g + 1] += __shfl_sync(0xffffffffu, breg.y, src);
+                        v[4 * g + 2] += __shfl_sync(0xffffffffu, breg.z, src);
+                        v[4 * g + 3] += __shfl_sync(0xffffffffu, breg.w, src);
                     }
                 }
                 if constexpr (EPI == EPI_BIAS_F16) {
@@ -457,8 +498,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 }
                 // ---- the chunk buffer: buffer b was last read by the store of chunk gc - EPI_BUFS; at most EPI_BUFS - 1 newer groups may
                 //      still be pending
+#ifdef Q2W_GEMM_WALL
+                const unsigned long long wc1 = gtime();
+#endif
                 if (lane == 0) bulk_wait_group_read<EPI_BUFS - 1>();
                 __syncwarp();
+#ifdef Q2W_GEMM_WALL
+                const unsigned long long wc2 = gtime();
+#endif
                 // ---- write the 128-byte row of this chunk, 16-byte pieces XOR-swizzled like SWIZZLE_128B expects
                 if constexpr (F16OUT) {
 #pragma unroll
@@ -478,8 +525,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                         *reinterpret_cast<float4*>(buf + row_off + ((static_cast<uint32_t>(g) ^ sw) << 4)) =
                             make_float4(v[4 * g + 0], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
                 }
+#ifdef Q2W_GEMM_WALL
+                const unsigned long long wc3 = gtime();
+#endif
                 fence_proxy_async_smem();
                 __syncwarp();
+#ifdef Q2W_GEMM_WALL
+                const unsigned long long wc4 = gtime();
+#endif
                 if (lane == 0) {
                     if (n < p.N) {                                  // rows >= M / columns >= N are clipped by the TMA unit
                         if constexpr (REDUCE) tma_reduce_add_2d(&tmO, buf, n, m0);
@@ -487,14 +540,25 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     }
                     bulk_commit_group();
                 }
+#ifdef Q2W_GEMM_WALL
+                if (leader && ew == 0 && lane == 0 && cluster_id == 0)
+                    printf("GC N%d K%d chunk %d: ld+math %llu wait_buf %llu st.shared %llu fence %llu issue %llu ns\n", p.N, p.K, c, wc1 - wc0, wc2 - wc1, wc3 - wc2, wc4 - wc3, gtime() - wc4);
+#endif
             }
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
         }
         // shared memory must outlive the reads of the last stores; their global writes are ordinary outstanding memory operations of this
         // grid, complete and visible before any dependent grid passes its griddepcontrol.wait / starts in stream order
+#ifdef Q2W_GEMM_WALL
+        const unsigned long long w_issued = gtime();
+#endif
         if (lane == 0) bulk_wait_group_read<0>();
         __syncwarp();
+#ifdef Q2W_GEMM_WALL
+        if (leader && ew == 0 && lane == 0 && (cluster_id == 0 || cluster_id == num_clusters - 1))
+            printf("GW epi c%d/%d N%d K%d acc_ready %llu stores_issued %llu stores_read %llu\n", cluster_id, num_clusters, p.N, p.K, w_acc, w_issued, gtime());
+#endif
     }
 
     tc_fence_before();
@@ -503,6 +567,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         tc_fence_after();
         tmem_dealloc_cta2(tmem_base, TMEM_COLS);
     }
+#ifdef Q2W_GEMM_WALL
+    if (leader && threadIdx.x == 0 && (cluster_id == 0 || cluster_id == num_clusters - 1))
+        printf("GW end c%d/%d N%d K%d exit %llu\n", cluster_id, num_clusters, p.N, p.K, gtime());
+#endif
 }
 
 // ------------------------------------------------------------------ host side

@@ -4,7 +4,8 @@ Restates, for the three on-path types only, what examples/common-ggml.cpp:41 (gg
 ggml_quantize_chunk: row-wise blocks of 32 along ne[0].
   block_q8_0 {f16 d; int8 qs[32]}  34 B   ggml/src/ggml-common.h:186-191   quantize_row_q8_0_ref ggml-quants.c:848-871
   block_q4_0 {f16 d; u8  qs[16]}   18 B   ggml/src/ggml-common.h:144-148   quantize_row_q4_0_ref ggml-quants.c:668-703
-tests/test_quant_cpu.py pins these bit-for-bit against the reference's own ggml_quantize_chunk (oracle/_ref).
+tests/test_host_cpu.py pins these bit-for-bit against the reference's own ggml_quantize_chunk: live (oracle/_ref,
+test_quantisers_bit_exact_vs_ggml) and against blocks it produced once (tests/golden/ggml_quant_blocks.npz).
 """
 from __future__ import annotations
 

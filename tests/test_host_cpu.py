@@ -110,6 +110,18 @@ def test_quantisers_bit_exact_vs_ggml(ref):
         assert np.array_equal(gq.dequantize(mine, t, 1280).reshape(-1), ref.ref_dequantize(theirs, t, x.size))
 
 
+def test_quantisers_bit_exact_vs_committed_ggml_blocks():
+    """the same pin without oracle/_ref: blocks produced once by the reference's ggml_quantize_chunk / dequantize_row_* (inputs with an
+    all-zero block, an outlier, a negative |max| tie and half-way roundings), committed as tests/golden/ggml_quant_blocks.npz"""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "ggml_quant_blocks.npz"))
+    x = g["x"]
+    for t in (gq.GGML_TYPE_Q8_0, gq.GGML_TYPE_Q4_0):
+        nm = gq.TYPE_NAMES[t]
+        mine = gq.quantize(x, t).reshape(-1)
+        assert np.array_equal(mine, g[f"raw_{nm}"]), nm
+        assert np.array_equal(gq.dequantize(mine, t, x.shape[1]).reshape(-1), g[f"deq_{nm}"]), nm
+
+
 def test_model_file_round_trip_and_reference_loads_it(ref):
     for wt in (gq.GGML_TYPE_F16, gq.GGML_TYPE_Q8_0, gq.GGML_TYPE_Q4_0, gq.GGML_TYPE_F32):
         mf = synth.synth_model(synth.TINY_HPARAMS, wt, seed=5)

@@ -79,3 +79,24 @@ def test_encoder_restatement_offsets_vs_live_reference(ref):
         emb = orc.encode(mel_np.window(mel, off_ms // 10, 100))
         assert rel_l2(emb, ctx.get_embeddings()) < 1e-3
     ctx.free()
+
+
+def test_restatement_full_size_on_samples_jfk_vs_golden():
+    """the oracle pinned at the size and on the input BASELINE configs[0] names: full model (32 layers, d = 1280), samples/jfk
+    (tests/golden/jfk_16k.wav) -- mel of all five fullset clips and the encoder on the speech clip against the reference's output"""
+    import wave
+    g = np.load(os.path.join(GOLD, "fullset_f16.npz"))
+    with wave.open(os.path.join(GOLD, "jfk_16k.wav")) as w:
+        jfk = (np.frombuffer(w.readframes(w.getnframes()), dtype=np.int16).astype(np.float32) / np.float32(32768.0)).astype(np.float32)
+    filters = synth.slaney_mel_filters(128)
+    clips = {"chirp": synth.synth_pcm(480000, seed=0), "ragged": synth.synth_pcm(250001, seed=5, kind="chirp"),
+             "silence": synth.synth_pcm(480000, seed=0, kind="silence"), "tones": synth.synth_pcm(480000, seed=0, kind="tones"), "jfk": jfk}
+    for name, pcm in clips.items():
+        mel = mel_np.log_mel_spectrogram(pcm, filters)
+        assert max_abs(mel[g["mel_row_idx"]][:, :3000], g[f"{name}_mel_rows"]) < 5e-5, name
+    mf = synth.synth_model(synth.FULL_HPARAMS, WT["f16"], seed=1234)
+    mel = mel_np.log_mel_spectrogram(jfk, mf.filters)
+    emb = encoder_np.EncoderOracle(mf, "ggml").encode(mel_np.window(mel, 0, 1500))
+    rows, want = emb[g["row_idx"]], g["jfk_emb_rows"]
+    assert rel_l2(rows, want) < 1e-3, rel_l2(rows, want)
+    assert np.abs(np.linalg.norm(emb.astype(np.float64), axis=1) / g["jfk_row_norm"] - 1.0).max() < 2e-3
