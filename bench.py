@@ -169,6 +169,7 @@ def main():
     ap.add_argument("--max-batch", type=int, default=0, help="windows per micro-batch (default: = --windows)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-latency", action="store_true", help="skip the B = 1 latency leg (ncu launch lists of the throughput step)")
     ap.add_argument("--no-second-wtype", action="store_true", help="skip the short pass with the other weight type (Q8_0 next to F16)")
     ap.add_argument("--cpu-threads", type=int, default=0)
     a = ap.parse_args()
@@ -241,7 +242,7 @@ def main():
     api.log_set(lambda lvl, txt: None)
 
     env = dict(rank=rank, local_rank=local_rank, world=world, threads=threads)
-    main_run = measure(a.wtype, a.windows, a.steps, a.warmup, a.max_batch, env, latency=True, total_windows=a.total_windows)
+    main_run = measure(a.wtype, a.windows, a.steps, a.warmup, a.max_batch, env, latency=not a.no_latency, total_windows=a.total_windows)
     # the metric names F16 AND Q8_0: a short second pass with the other weight type, same batch, same kernels (BASELINE configs[2] shape per GPU)
     second = None
     if not a.no_second_wtype and not a.total_windows:
