@@ -211,6 +211,51 @@ dequant_q4_0_kernel(const uint8_t* __restrict__ src, __half* __restrict__ dst, s
     for (int j = 0; j < 4; ++j) out[j] = reinterpret_cast<const uint4*>(o)[j];
 }
 
+// One launch decodes up to four matrices (a whole encoder block: QKV | out | fc1 | fc2). Four threads per 32-element ggml block, one
+// 16-byte store each: a warp writes 512 contiguous bytes (whole sectors), and reads its 8 blocks' 272 / 144 contiguous bytes.
+// Values are bit-identical to dequant_q8_0 / q4_0_kernel above: F16(q * d) with one rounding.
+template <int TYPE>
+__global__ void __launch_bounds__(256)
+dequant_multi_kernel(const DequantJob job, unsigned long long total_threads) {
+    pdl_wait();
+    pdl_launch_dependents();
+    // grid-stride over a SMALL grid (two CTAs per SM): this kernel runs on the decode stream next to the compute stream's GEMMs, and a
+    // grid that fills every thread slot of the machine keeps their CTAs (one per SM, 213 KB of shared memory) from launching at all
+    for (unsigned long long gid = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x; gid < total_threads;
+         gid += static_cast<unsigned long long>(gridDim.x) * blockDim.x) {
+        unsigned long long blk = gid >> 2;
+        const int part = static_cast<int>(gid & 3);
+        int t = 0;
+        while (t < 3 && blk >= job.nblocks[t]) { blk -= job.nblocks[t]; ++t; }
+        __align__(16) __half o[8];
+        if constexpr (TYPE == 8) {
+            const uint16_t* p = reinterpret_cast<const uint16_t*>(job.src[t] + blk * 34);   // {f16 d; int8 qs[32]}
+            const float d = __half2float(__ushort_as_half(__ldg(p)));
+            uint16_t w[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) w[j] = __ldg(p + 1 + part * 4 + j);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                o[2 * j]     = __float2half_rn(static_cast<float>(static_cast<int8_t>(w[j] & 0xFF)) * d);
+                o[2 * j + 1] = __float2half_rn(static_cast<float>(static_cast<int8_t>(w[j] >> 8)) * d);
+            }
+        } else {
+            const uint16_t* p = reinterpret_cast<const uint16_t*>(job.src[t] + blk * 18);   // {f16 d; u8 qs[16]}: element j low nibble of qs[j], j + 16 high
+            const float d = __half2float(__ushort_as_half(__ldg(p)));
+            const int sh = (part >> 1) * 4;
+            uint16_t w[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) w[j] = __ldg(p + 1 + (part & 1) * 4 + j);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                o[2 * j]     = __float2half_rn(static_cast<float>((((w[j] & 0xFF) >> sh) & 0xF) - 8) * d);
+                o[2 * j + 1] = __float2half_rn(static_cast<float>((((w[j] >> 8) >> sh) & 0xF) - 8) * d);
+            }
+        }
+        *reinterpret_cast<uint4*>(job.dst[t] + blk * 32 + part * 8) = *reinterpret_cast<const uint4*>(o);
+    }
+}
+
 __global__ void __launch_bounds__(256)
 f32_to_f16_kernel(const float* __restrict__ src, __half* __restrict__ dst, size_t n) {
     pdl_wait();               // predecessor grid complete + visible (launch.cuh)
@@ -254,6 +299,23 @@ cudaError_t conv2_im2col(const __half* h1, __half* A2, int B, int T2, int C, cud
     size_t blocks = (total + 255) / 256;
     if (blocks > 148 * 32) blocks = 148 * 32;
     return launch_pdl(conv2_im2col_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, st, h1, A2, B, T2, C);
+}
+
+cudaError_t dequant_multi_to_f16(const DequantJob& job, int ggml_type, cudaStream_t st) {
+    unsigned long long total = 0;
+    for (int i = 0; i < 4; ++i) total += job.nblocks[i];
+    if (total == 0) return cudaSuccess;
+    const unsigned long long threads = total * 4;
+    DeviceInfo di;
+    cudaError_t e = current_device_info(di);
+    if (e != cudaSuccess) return e;
+    const unsigned long long want = (threads + 255) / 256;
+    const unsigned grid = static_cast<unsigned>(want < 2ull * di.num_sms ? want : 2ull * di.num_sms);
+    switch (ggml_type) {
+        case 8: return launch_pdl(dequant_multi_kernel<8>, dim3(grid), dim3(256), 0, st, job, threads);
+        case 2: return launch_pdl(dequant_multi_kernel<2>, dim3(grid), dim3(256), 0, st, job, threads);
+        default: return cudaErrorInvalidValue;
+    }
 }
 
 cudaError_t dequant_to_f16(const void* src, int ggml_type, __half* dst, size_t rows, int K, cudaStream_t st) {

@@ -117,7 +117,11 @@ struct q2w_state {
     __half* qkv = nullptr;     // [B*T, 3D]        (aliases conv2 operand A2)
     __half* att = nullptr;     // [B*T, D]         (aliases conv1 operand A1)
     __half* h = nullptr;       // [B*T, 4D]        (aliases conv1 output h1 [B*T2, D])
-    __half* wscratch = nullptr;  // decoded weight matrix (largest: 4D*D)
+    // quantised weights: one encoder block (QKV | out | fc1 | fc2) decoded to F16 per launch, double-buffered, on a side stream one
+    // block ahead of the compute stream
+    __half* wlayer[2] = {nullptr, nullptr};
+    cudaStream_t s_dq = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_dq[2] = {nullptr, nullptr}, ev_lay[2] = {nullptr, nullptr};
     float* pcm_dev = nullptr;  // [2][B, win_samples]  double-buffered host staging (copy of micro-batch i+1 overlaps compute of i)
     int* nsamp_dev = nullptr;  // [2][B]
     cudaStream_t s_in = nullptr, s_out = nullptr;   // copy-in / copy-out streams of the host-buffer batch path
@@ -128,7 +132,7 @@ struct q2w_state {
     bool att_sched_dirty = false;   // a forward pass failed part-way: re-zero the counter before the next launch
     int dbg_layers = -1;       // q2w_debug_forward_layers: stop after this many encoder blocks (-1 = all); eager launches only
     int dbg_windows = 0;       // windows of the last forward still resident in x
-    int fused_dequant = -1;    // Q2W_FUSED_DEQUANT: 1 always in-kernel decode, 0 always scratch, -1 pick by M
+    int fused_dequant = 0;     // Q2W_FUSED_DEQUANT=1: in-kernel decode (A/B); default: one decode launch per block on the side stream
     int e2e_split = 2;         // Q2W_E2E_SPLIT: micro-batches a synchronous host batch is cut into
     // asynchronous host batches: at most two in flight; ticket t owns embedding region t & 1 and completion event ev_ticket[t & 1]
     cudaEvent_t ev_ticket[2] = {nullptr, nullptr};
@@ -194,8 +198,9 @@ int check_device(int device) {
 
 struct ProfScope {
     q2w_state* s;
+    cudaStream_t st;
     long idx = -1;   // index, not pointer: the record vector may grow while a scope is open
-    ProfScope(q2w_state* s_, int cls, double flops, double bytes) : s(s_) {
+    ProfScope(q2w_state* s_, int cls, double flops, double bytes, cudaStream_t st_ = nullptr) : s(s_), st(st_ ? st_ : s_->stream) {
         if (!s->prof_on) return;
         if (s->prof_used == s->prof.size()) {
             q2w_state::ProfRec n{};
@@ -205,42 +210,45 @@ struct ProfScope {
         idx = static_cast<long>(s->prof_used++);
         q2w_state::ProfRec& r = s->prof[idx];
         r.cls = cls; r.flops = flops; r.bytes = bytes;
-        cudaEventRecord(r.a, s->stream);
+        cudaEventRecord(r.a, st);
     }
-    ~ProfScope() { if (idx >= 0) cudaEventRecord(s->prof[idx].b, s->stream); }
+    ~ProfScope() { if (idx >= 0) cudaEventRecord(s->prof[idx].b, st); }
 };
-// largest M for which the in-kernel decode beats decode-to-scratch + F16 GEMM (measured at M = 1500: see DESIGN.md section 5)
-constexpr int kFusedDequantMaxM = 0;
 enum { PC_GEMM = 0, PC_ATTN = 1, PC_LN = 2, PC_MEL = 3, PC_IM2COL = 4, PC_DEQUANT = 5, PC_COUNT = 6 };
 
-// y = A x W^T with W in the model's device type: quantised matrices are decoded to f16 into the (L2-resident) scratch first
-int weight_gemm(q2w_state* s, const __half* A, int lda, const void* W, int wtype_dev, int M, int N, int K, const float* bias,
+// y = A x W^T.  wtype: F16 (TMA-fed W) or Q8_0 / Q4_0 raw ggml blocks (decoded by the GEMM's own dequant warpgroup).
+// w_static: W is a model tensor no kernel writes (its first tiles may be fetched before the previous kernel has finished).
+int weight_gemm(q2w_state* s, const __half* A, int lda, const void* W, int wtype, bool w_static, int M, int N, int K, const float* bias,
                 void* out, int ldo, GemmEpilogue epi, const float* resid, const float* pos, int pos_period, int scale_cols,
                 float scale) {
-    const __half* Wh = static_cast<const __half*>(W);
-    int gemm_wtype = Q2W_TYPE_F16;
-    if (wtype_dev != Q2W_TYPE_F16) {
-        // Two decode strategies, both keep W quantised in HBM (measured on B200):
-        //   fused   raw ggml blocks go straight into the GEMM and are decoded by its dequant warpgroup:
-        //           every W tile is re-decoded by each M-tile that uses it -- 2.7x slower at M = 96000 (750 M-tiles per W tile)
-        //   scratch one decode pass per GEMM into a 13 MB L2-resident F16 scratch, then the TMA-fed F16 GEMM:
-        //           1205 TFLOP/s at B = 64, the decode pass costs 1 % of the step
-        // Selected by M (few M-tiles per W tile -> the decode launch and the scratch round trip weigh more); Q2W_FUSED_DEQUANT=0/1 forces one.
-        const bool fused = s->fused_dequant >= 0 ? s->fused_dequant != 0 : M <= kFusedDequantMaxM;
-        if (fused && K % 64 == 0) {
-            gemm_wtype = wtype_dev;
-        } else {
-            ProfScope ps(s, PC_DEQUANT, 0.0, static_cast<double>(type_row_bytes(wtype_dev, K)) * N + 2.0 * N * K);
-            CKL(dequant_to_f16(W, wtype_dev, s->wscratch, static_cast<size_t>(N), K, s->stream));
-            Wh = s->wscratch;
-        }
-    }
     ProfScope ps(s, PC_GEMM, 2.0 * M * static_cast<double>(N) * K, 0.0);
     GemmArgs g{};
-    g.A = A; g.lda = lda; g.W = Wh; g.ldw = K; g.wtype = gemm_wtype; g.M = M; g.N = N; g.K = K; g.bias = bias; g.out = out; g.ldo = ldo;
+    g.A = A; g.lda = lda; g.W = static_cast<const __half*>(W); g.ldw = K; g.wtype = wtype; g.M = M; g.N = N; g.K = K; g.bias = bias; g.out = out; g.ldo = ldo;
     g.resid = resid; g.pos = pos; g.pos_period = pos_period; g.scale_cols = scale_cols; g.scale = scale;
-    g.w_static = Wh != s->wscratch;     // model weights are immutable; the decode scratch is written by the kernel just before this one
+    g.w_static = w_static ? 1 : 0;
     CKL(gemm_f16_tcgen05(g, epi, s->stream));
+    return Q2W_OK;
+}
+
+// the four weight matrices of encoder block il, decoded to F16 into layer buffer `buf` by ONE launch on the decode stream
+int decode_layer(q2w_state* s, int il, int buf) {
+    q2w_model* m = s->m;
+    Layer& L = m->layers[il];
+    const size_t D = s->D, FF = s->FF;
+    DequantJob job{};
+    const void* src[4] = {L.qkv_w, L.o_w.d, L.fc1_w.d, L.fc2_w.d};
+    const size_t elems[4] = {3 * D * D, D * D, FF * D, D * FF};
+    size_t off = 0;
+    double in_bytes = 0;
+    for (int i = 0; i < 4; ++i) {
+        job.src[i] = static_cast<const uint8_t*>(src[i]);
+        job.dst[i] = s->wlayer[buf] + off;
+        job.nblocks[i] = elems[i] / 32;
+        off += elems[i];
+        in_bytes += static_cast<double>(elems[i] / 32) * (m->wtype_dev == Q2W_TYPE_Q8_0 ? 34 : 18);
+    }
+    ProfScope ps(s, PC_DEQUANT, 0.0, in_bytes + 2.0 * off, s->s_dq);
+    CKL(dequant_multi_to_f16(job, m->wtype_dev, s->s_dq));
     return Q2W_OK;
 }
 
@@ -301,7 +309,7 @@ int forward_eager(q2w_state* s, int Bm, int w0) {
     __half* A2 = s->qkv;
     int rc;
     // conv1 (k3 s1 p1) + bias + GELU   (:1922-1925)
-    if ((rc = weight_gemm(s, A1, 3 * s->n_mel, m->conv1_w.d, Q2W_TYPE_F16, Bm * T2, D, 3 * s->n_mel,
+    if ((rc = weight_gemm(s, A1, 3 * s->n_mel, m->conv1_w.d, Q2W_TYPE_F16, true, Bm * T2, D, 3 * s->n_mel,
                           static_cast<const float*>(m->conv1_b.d), h1, D, EPI_BIAS_GELU_F16, nullptr, nullptr, 0, 0, 1.f)))
         return rc;
     // conv2 (k3 s2 p1) + bias + GELU, transposed to time-major and + positional embedding   (:1927-1930, :2001-2005)
@@ -309,20 +317,53 @@ int forward_eager(q2w_state* s, int Bm, int w0) {
         ProfScope ps(s, PC_IM2COL, 0.0, 2.0 * Bm * (static_cast<double>(T2) * D + static_cast<double>(T) * 3 * D));
         CKL(conv2_im2col(h1, A2, Bm, T2, D, s->stream));
     }
-    if ((rc = weight_gemm(s, A2, 3 * D, m->conv2_w.d, Q2W_TYPE_F16, M, D, 3 * D, static_cast<const float*>(m->conv2_b.d),
+    if ((rc = weight_gemm(s, A2, 3 * D, m->conv2_w.d, Q2W_TYPE_F16, true, M, D, 3 * D, static_cast<const float*>(m->conv2_b.d),
                           s->x, D, EPI_BIAS_GELU_POS_F32, nullptr, static_cast<const float*>(m->pe.d), T, 0, 1.f)))
         return rc;
     const float kq_scale = 1.0f / sqrtf(static_cast<float>(D / H));  // :1985
     const int n_layers = s->dbg_layers >= 0 ? std::min(s->dbg_layers, m->hp.n_audio_layer) : m->hp.n_audio_layer;
+    // Quantised weights stay Q8_0 / Q4_0 in HBM exactly as in the model file. Two decode strategies:
+    //   layer   (default) one launch decodes a whole block's four matrices into a 39 MB F16 layer buffer on the decode stream, ONE BLOCK
+    //           AHEAD of the compute stream (two buffers): the GEMMs are the plain TMA-fed F16 kernels, the decode is off the critical
+    //           path at every batch size
+    //   fused   (Q2W_FUSED_DEQUANT=1) raw ggml blocks go straight into the GEMM and are decoded by its dequant warpgroup: every W tile
+    //           is re-decoded by each M-tile that uses it -- measured 2.7x slower at M = 96000 and 1.7x slower at M = 1500
+    const bool quant = m->wtype_dev != Q2W_TYPE_F16;
+    const bool fused = quant && s->fused_dequant > 0 && D % 64 == 0;
+    const bool by_layer = quant && !fused;
+    const size_t w_off[4] = {0, static_cast<size_t>(3) * D * D, static_cast<size_t>(4) * D * D, static_cast<size_t>(4) * D * D + static_cast<size_t>(FF) * D};
+    if (by_layer && n_layers > 0) {
+        CK(cudaEventRecord(s->ev_fork, s->stream));          // the decode stream joins this pass (and this capture)
+        CK(cudaStreamWaitEvent(s->s_dq, s->ev_fork, 0));
+        if ((rc = decode_layer(s, 0, 0))) return rc;
+        CK(cudaEventRecord(s->ev_dq[0], s->s_dq));
+    }
     for (int il = 0; il < n_layers; ++il) {
         Layer& L = m->layers[il];
+        const void* w_qkv = L.qkv_w; const void* w_o = L.o_w.d; const void* w_fc1 = L.fc1_w.d; const void* w_fc2 = L.fc2_w.d;
+        int wt = m->wtype_dev;
+        bool w_static = true;
+        if (by_layer) {
+            const int buf = il & 1;
+            if (il + 1 < n_layers) {
+                // buffer buf ^ 1 was last read by block il - 1
+                if (il >= 1) CK(cudaStreamWaitEvent(s->s_dq, s->ev_lay[buf ^ 1], 0));
+                if ((rc = decode_layer(s, il + 1, buf ^ 1))) return rc;
+                CK(cudaEventRecord(s->ev_dq[buf ^ 1], s->s_dq));
+            }
+            CK(cudaStreamWaitEvent(s->stream, s->ev_dq[buf], 0));
+            const __half* base = s->wlayer[buf];
+            w_qkv = base + w_off[0]; w_o = base + w_off[1]; w_fc1 = base + w_off[2]; w_fc2 = base + w_off[3];
+            wt = Q2W_TYPE_F16;
+            w_static = false;                                  // written by the decode kernel: never fetch it early
+        }
         // pre-LN + fused QKV projection (+bias, Q * KQscale)   (:2019-2055)
         {
             ProfScope ps(s, PC_LN, 0.0, 6.0 * M * D);
             CKL(layernorm_f32_to_f16(s->x, static_cast<const float*>(L.ln1_w.d), static_cast<const float*>(L.ln1_b.d), s->ln, M, D,
                                      eps, s->stream));
         }
-        if ((rc = weight_gemm(s, s->ln, D, L.qkv_w, m->wtype_dev, M, 3 * D, D, L.qkv_b, s->qkv, 3 * D, EPI_BIAS_F16, nullptr,
+        if ((rc = weight_gemm(s, s->ln, D, w_qkv, wt, w_static, M, 3 * D, D, L.qkv_b, s->qkv, 3 * D, EPI_BIAS_F16, nullptr,
                               nullptr, 0, D, kq_scale)))
             return rc;
         // softmax(Q K^T) V per head   (:2080-2106)
@@ -331,7 +372,7 @@ int forward_eager(q2w_state* s, int Bm, int w0) {
             CKL(attention_f16_tcgen05(s->qkv, s->att, Bm, T, H, s->att_sched, s->stream));
         }
         // out-proj + bias + residual   (:2112-2120)
-        if ((rc = weight_gemm(s, s->att, D, L.o_w.d, m->wtype_dev, M, D, D, static_cast<const float*>(L.o_b.d), s->x, D,
+        if ((rc = weight_gemm(s, s->att, D, w_o, wt, w_static, M, D, D, static_cast<const float*>(L.o_b.d), s->x, D,
                               EPI_BIAS_RESID_F32, s->x, nullptr, 0, 0, 1.f)))
             return rc;
         // MLP: LN, fc1 + GELU, fc2 + residual   (:2128-2154)
@@ -340,12 +381,13 @@ int forward_eager(q2w_state* s, int Bm, int w0) {
             CKL(layernorm_f32_to_f16(s->x, static_cast<const float*>(L.ln2_w.d), static_cast<const float*>(L.ln2_b.d), s->ln, M, D,
                                      eps, s->stream));
         }
-        if ((rc = weight_gemm(s, s->ln, D, L.fc1_w.d, m->wtype_dev, M, FF, D, static_cast<const float*>(L.fc1_b.d), s->h, FF,
+        if ((rc = weight_gemm(s, s->ln, D, w_fc1, wt, w_static, M, FF, D, static_cast<const float*>(L.fc1_b.d), s->h, FF,
                               EPI_BIAS_GELU_F16, nullptr, nullptr, 0, 0, 1.f)))
             return rc;
-        if ((rc = weight_gemm(s, s->h, FF, L.fc2_w.d, m->wtype_dev, M, D, FF, static_cast<const float*>(L.fc2_b.d), s->x, D,
+        if ((rc = weight_gemm(s, s->h, FF, w_fc2, wt, w_static, M, D, FF, static_cast<const float*>(L.fc2_b.d), s->x, D,
                               EPI_BIAS_RESID_F32, s->x, nullptr, 0, 0, 1.f)))
             return rc;
+        if (by_layer) CK(cudaEventRecord(s->ev_lay[il & 1], s->stream));
     }
     // avg-pool(2,2) over time + final LayerNorm   (:2160-2181)
     float* out = s->emb + static_cast<size_t>(w0) * (T / 2) * D;
@@ -633,16 +675,24 @@ int q2w_state_create(q2w_state** out, q2w_model* m, int max_batch) {
     s->n_frames_batch = s->T2 + 2;                      // frames T2, T2+1 still see real samples and enter the max (:2522, :2634)
     s->ld_mel = (s->n_frames_batch + 15) / 16 * 16;
     const size_t D = s->D;
-    const size_t wmax = std::max<size_t>(static_cast<size_t>(4) * D * D, 3 * D * D);
+    const size_t wlayer_elems = static_cast<size_t>(12) * D * D;     // QKV 3 D^2 + out D^2 + fc1 4 D^2 + fc2 4 D^2
     {   // decode strategy for quantised weights, resolved once per state
         const char* e = getenv("Q2W_FUSED_DEQUANT");
-        s->fused_dequant = e ? atoi(e) : -1;             // -1: pick by M (weight_gemm)
+        s->fused_dequant = e ? atoi(e) : 0;              // 1: decode inside the GEMM; 0 (default): per-block decode on the side stream
         const char* sp = getenv("Q2W_E2E_SPLIT");
         s->e2e_split = sp ? std::max(1, atoi(sp)) : 2;
     }
     cudaError_t e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = alloc_workspaces(s, max_batch);
-    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&s->wscratch), wmax * sizeof(__half));
+    if (m->wtype_dev != Q2W_TYPE_F16) {
+        for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+            e = cudaMalloc(reinterpret_cast<void**>(&s->wlayer[i]), wlayer_elems * sizeof(__half));
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_dq[i], cudaEventDisableTiming);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_lay[i], cudaEventDisableTiming);
+        }
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->s_dq, cudaStreamNonBlocking);
+    }
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->s_in, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->s_out, cudaStreamNonBlocking);
     for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
@@ -696,8 +746,15 @@ void q2w_state_free(q2w_state* s) {
     if (s->s_in) cudaStreamSynchronize(s->s_in);      // asynchronous batches may still be copying from / into caller memory
     if (s->s_out) cudaStreamSynchronize(s->s_out);
     free_workspaces(s);
-    void* ptrs[] = {s->wscratch, s->emb, s->api_mel, s->api_pcm, s->api_max, s->att_sched};
+    if (s->s_dq) cudaStreamSynchronize(s->s_dq);
+    void* ptrs[] = {s->wlayer[0], s->wlayer[1], s->emb, s->api_mel, s->api_pcm, s->api_max, s->att_sched};
     for (void* p : ptrs) if (p) cudaFree(p);
+    for (int i = 0; i < 2; ++i) {
+        if (s->ev_dq[i]) cudaEventDestroy(s->ev_dq[i]);
+        if (s->ev_lay[i]) cudaEventDestroy(s->ev_lay[i]);
+    }
+    if (s->ev_fork) cudaEventDestroy(s->ev_fork);
+    if (s->s_dq) cudaStreamDestroy(s->s_dq);
     for (auto& r : s->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (int i = 0; i < 2; ++i) {
         if (s->ev_in[i]) cudaEventDestroy(s->ev_in[i]);

@@ -74,5 +74,12 @@ cudaError_t conv2_im2col(const __half* h1, __half* A2, int B, int T2, int C, cud
 
 // ---- ggml block decode: Q8_0 / Q4_0 / F32 rows -> f16 [rows, K] (K % 32 == 0)
 cudaError_t dequant_to_f16(const void* src, int ggml_type, __half* dst, size_t rows, int K, cudaStream_t st);
+// up to four matrices (one encoder block) in ONE launch: src[i] raw ggml blocks (Q8_0 = 8 / Q4_0 = 2), dst[i] f16, nblocks[i] 32-element blocks
+struct DequantJob {
+    const uint8_t* src[4];
+    __half* dst[4];
+    unsigned long long nblocks[4];
+};
+cudaError_t dequant_multi_to_f16(const DequantJob& job, int ggml_type, cudaStream_t st);
 
 }  // namespace q2w
