@@ -1,6 +1,6 @@
 // q2w-main -- the reference CLI (examples/main/main.cpp) on the B200 library, through the public API only.
 //
-//   q2w-main -m model.bin -f audio.wav [-n iters] [-ot offset_ms] [-d duration_ms] [-dev gpu] [--long] [-np]
+//   q2w-main -m model.bin -f audio.wav [-n iters] [-ot offset_ms] [-d duration_ms] [-dev gpu | -dev -1 (all GPUs)] [--long] [-np]
 //
 // Mirrors /root/reference/examples/main/main.cpp:353-594 for the part of it that reaches the encoder: read a 16-bit
 // 16 kHz mono/stereo WAV (read_wav, examples/common.cpp:642-748: int16 / 32768, stereo averaged), init from file,

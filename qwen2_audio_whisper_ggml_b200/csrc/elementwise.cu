@@ -32,9 +32,13 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, c
                  OutT* __restrict__ y, int rows_out, int D, float eps, int T /*POOL: input rows per window*/) {
     pdl_wait();               // predecessor grid complete + visible (launch.cuh)
     pdl_launch_dependents();
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int widx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    if (warp >= rows_out) return;
+    if (widx >= rows_out) return;
+    // Rows are taken LAST FIRST. The producer (a persistent GEMM walking its tiles in row order) wrote the last rows of x most recently,
+    // so at large M (x = 491 MB at 64 windows, L2 = 126 MB) they are the ones still in L2; and the consumer GEMM starts at row 0, which
+    // this order writes last. Same bytes, fewer of them from HBM.
+    const int warp = rows_out - 1 - widx;
     const int nvec = D >> 2;
     const float4* src0;
     const float4* src1 = nullptr;
