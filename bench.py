@@ -242,12 +242,16 @@ def main():
     api.log_set(lambda lvl, txt: None)
 
     env = dict(rank=rank, local_rank=local_rank, world=world, threads=threads)
-    main_run = measure(a.wtype, a.windows, a.steps, a.warmup, a.max_batch, env, latency=not a.no_latency, total_windows=a.total_windows)
-    # the metric names F16 AND Q8_0: a short second pass with the other weight type, same batch, same kernels (BASELINE configs[2] shape per GPU)
-    second = None
-    if not a.no_second_wtype and not a.total_windows:
-        other = "q8_0" if a.wtype == "f16" else "f16"
-        second = measure(other, a.windows, max(2, min(a.steps, 3)), 2, a.max_batch, env, latency=True, total_windows=0)
+    # BASELINE configs[2]-[4] ride along as short strong-scaling passes (fixed total number of windows, sharded over the ranks), so
+    # that one default run -- and the driver's 1/2/4/8-GPU runs of it -- records every configuration the metric names:
+    #   F16 context:  + 120 windows (1 h of audio, configs[4]);   Q8_0 context: weak pass + 256 windows (configs[2]);   Q4_0: 256 (configs[3])
+    full = not a.no_second_wtype and not a.total_windows
+    main_run = measure(a.wtype, a.windows, a.steps, a.warmup, a.max_batch, env, latency=not a.no_latency, total_windows=a.total_windows,
+                       extra_totals=(120,) if full and a.wtype == "f16" else ())
+    others = []
+    if full:
+        for other, totals in (("q8_0", (256,)), ("q4_0", (256,))) if a.wtype == "f16" else (("f16", ()),):
+            others.append(measure(other, a.windows, max(2, min(a.steps, 3)), 2, a.max_batch, env, latency=True, total_windows=0, extra_totals=totals))
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
@@ -263,11 +267,21 @@ def main():
     if rank == 0:
         line = assemble(main_run, a, world, scaling, config)
         line["cpu_baseline"] = cpu_baseline
-        if second is not None:
-            s2 = assemble(second, a, world, scaling, dict(config, weights=second["wtype"]))
-            line["configs"] = {f"{second['wtype']}_b{a.windows}": {k: s2[k] for k in ("value", "unit", "ms_per_step", "dtype", "e2e", "roofline", "kernels", "parity",
-                                                                                      "p50_ms_per_window_b1", "steps", "warmup", "gpu_launches")}}
-        ok = all(p_.get("ok", True) for r_ in (main_run, second) if r_ for p_ in r_["parity"].values() if p_.get("checked"))
+        cfgs = {}
+        for r_ in [main_run] + others:
+            if r_ is not main_run:
+                s2 = assemble(r_, a, world, scaling, dict(config, weights=r_["wtype"]))
+                cfgs[f"{r_['wtype']}_weak_{a.windows}_per_gpu"] = {k: s2[k] for k in ("value", "unit", "ms_per_step", "dtype", "e2e", "roofline", "kernels", "parity",
+                                                                                     "p50_ms_per_window_b1", "steps", "warmup", "gpu_launches")}
+            for T, x in r_["extras"].items():
+                cfgs[f"{r_['wtype']}_total_{T}_windows"] = {
+                    "workload": f"{T} x 30 s windows ({T * 30 / 3600:.2f} h of audio) in total, {r_['wtype'].upper()} weights, sharded over {world} GPU(s) (strong scaling)",
+                    "value": x["value"], "unit": UNIT, "ms_per_pass": x["ms_per_pass"], "steps": x["steps"], "scaling": "strong",
+                    "e2e": {"value": x["e2e_value"], "unit": UNIT, "ms_per_pass": x["e2e_ms_per_pass"], "h2d_bytes_per_step": x["h2d"], "d2h_bytes_per_step": x["d2h"]},
+                    "windows_rank0": x["windows_this_rank"], "parity": x["parity"]}
+        if cfgs:
+            line["configs"] = cfgs
+        ok = all(p_.get("ok", True) for r_ in [main_run] + others for p_ in r_["parity"].values() if p_.get("checked"))
         line["parity_ok"] = ok
         print(json.dumps(line))
     if world > 1:
@@ -276,7 +290,7 @@ def main():
         raise SystemExit("bench.py: the benchmarked outputs do NOT match the reference golden (see \"parity\" in the line above)")
 
 
-def measure(wtype: str, B: int, steps: int, warmup: int, max_batch: int, env: dict, latency: bool, total_windows: int) -> dict:
+def measure(wtype: str, B: int, steps: int, warmup: int, max_batch: int, env: dict, latency: bool, total_windows: int, extra_totals=()) -> dict:
     """one weight type through every leg: B = 1 latency, device-resident throughput with the live per-kernel profile, end to end
     with host buffers -- and a golden check of window 0 after each of them"""
     import ctypes as C
@@ -413,11 +427,63 @@ def measure(wtype: str, B: int, steps: int, warmup: int, max_batch: int, env: di
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms, e2e_s = float(t[0]), float(t[1])
     h2d, d2h = int(host.numel() * 4), int(outs[0].numel() * 4)
+
+    # ---- the other BASELINE configurations on the same context: a fixed TOTAL number of windows sharded over the ranks (strong scaling;
+    #      configs[2]/[3]: 256 windows, configs[4]: 1 h of audio = 120 windows), larger than max_batch -> chunked into micro-batches
+    extras = {}
+    for T in extra_totals:
+        from qwen2_audio_whisper_ggml_b200.parallel import shard_bounds
+        lo, hi = shard_bounds(T, rank, world)
+        n = hi - lo
+        reps = -(-n // B)
+        xh = host.repeat(reps, 1)[:n].contiguous().pin_memory() if n > 0 else None
+        xd = xh.cuda() if n > 0 else None
+        xo = [torch.empty((max(n, 1), 750, 1280), dtype=torch.float32).pin_memory() for _ in range(2)]
+        def xdev():
+            if n > 0 and ctx.encode_batch_device(xd.data_ptr(), 480000, n) != 0:
+                raise RuntimeError("whisper_encode_batch_device failed")
+        def xhost(k):
+            prev = None
+            for i in range(k):
+                if n == 0:
+                    continue
+                tk = ctx.encode_batch_async(xh.numpy(), xo[i & 1][:n].numpy())
+                if prev is not None:
+                    ctx.wait(prev)
+                prev = tk
+            if prev is not None:
+                ctx.wait(prev)
+        xsteps = 3
+        for _ in range(2):
+            xdev()
+        barrier()
+        x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        x0.record(stream)
+        for _ in range(xsteps):
+            xdev()
+        x1.record(stream)
+        barrier()
+        x_ms = x0.elapsed_time(x1)
+        par = golden_check(window0_device(), wtype) if n > 0 else {"checked": False, "why": "empty shard"}
+        xhost(1)
+        barrier()
+        tx = time.perf_counter()
+        xhost(xsteps)
+        barrier()
+        x_e2e = time.perf_counter() - tx
+        tt = torch.tensor([x_ms, x_e2e], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        extras[T] = dict(total_windows=T, windows_this_rank=n, steps=xsteps, ms_per_pass=float(tt[0]) / xsteps,
+                         value=WINDOW_S * T * xsteps / (float(tt[0]) / 1e3), e2e_value=WINDOW_S * T * xsteps / float(tt[1]),
+                         e2e_ms_per_pass=1e3 * float(tt[1]) / xsteps, parity=par, h2d=int(n) * 480000 * 4, d2h=int(n) * 750 * 1280 * 4)
+        parity[f"total{T}_device_batch"] = par
+        del xh, xd, xo
     ctx.free()
     del dev, host, outs
     torch.cuda.empty_cache()
     return dict(wtype=wtype, B=B, steps=steps, warmup=warmup, dev_ms=dev_ms, e2e_s=e2e_s, launches=int(launches), clocks=clocks, prof=prof, lat=lat,
-                parity=parity, gather_ms=gather_ms, setup_s=setup_s, h2d=h2d, d2h=d2h, total_windows=total_windows)
+                parity=parity, gather_ms=gather_ms, setup_s=setup_s, h2d=h2d, d2h=d2h, total_windows=total_windows, extras=extras)
 
 
 def assemble(r: dict, a, world: int, scaling: str, config: dict) -> dict:
