@@ -129,6 +129,18 @@ Q2W_API int  q2w_profile_read(q2w_state* s, int kernel_class, double* total_ms, 
 Q2W_API void* q2w_state_stream(const q2w_state* s);
 Q2W_API int  q2w_sync(q2w_state* s);
 
+/* ---- the step after the path, additive and optional -------------------------------- */
+/* Qwen2-Audio's multi_modal_projector: Linear(n_audio_state -> n_out) + bias on every embedding row (HF
+ * Qwen2AudioMultiModalProjector.linear; the reference stops at the final LayerNorm, src/qwen2-whisper.cpp:2175-2185).
+ * W: [n_out][n_audio_state] row-major, F32 or F16 (rounded to F16 once); bias float[n_out] or NULL.  Once uploaded, the pool +
+ * final-LayerNorm kernel also writes its rows in F16 (same pass) and q2w_project runs one tcgen05 GEMM over the embeddings of
+ * the last encode / encode_batch: float[n_windows * n_audio_ctx/2][n_out], kept on the device, copied to out_host if non-NULL. */
+Q2W_API int  q2w_model_upload_projector(q2w_model* m, int ggml_type, int n_out, const void* w_host, size_t nbytes, const float* bias_host);
+Q2W_API int  q2w_model_projector_width(const q2w_model* m);
+Q2W_API int  q2w_project(q2w_state* s, float* out_host, size_t n_floats);
+Q2W_API int  q2w_projection_dims(const q2w_state* s, int* n_rows, int* n_out);
+Q2W_API const float* q2w_projected_device(const q2w_state* s);
+
 /* ---- all GPUs of the box from one process (SURVEY 8(b) additive item 3, 8(e)) -------------------- */
 /* One weight replica per device (the caller creates and uploads one q2w_model per device; the same device may be listed more than
  * once -- replicas are independent), one state + one host worker thread per replica.  A batch is cut into contiguous blocks, window

@@ -231,6 +231,12 @@ WHISPER_API int whisper_device   (struct whisper_context * ctx, int i);
 WHISPER_API int whisper_encode_batch_multi(struct whisper_context * ctx, const float * samples, size_t stride, const int32_t * n_samples, int n_windows, float * dst, int gather_device);
 WHISPER_API const float * whisper_get_gathered_device(struct whisper_context * ctx);
 WHISPER_API void * whisper_q2w_multi(struct whisper_context * ctx);   /* q2w_multi* (include/q2w_b200.h) or NULL */
+/* the step after the path: Qwen2-Audio's multi_modal_projector, Linear(n_audio_state -> n_out) + bias, applied to the
+ * embeddings of the last encode by one more tcgen05 GEMM.  weight: [n_out][n_audio_state] row-major, ggml_type 0 (F32) or 1 (F16);
+ * bias float[n_out] or NULL.  whisper_project -> float[n_windows * n_audio_ctx/2][n_out] (copied to dst if non-NULL). */
+WHISPER_API int whisper_set_projector(struct whisper_context * ctx, int ggml_type, int n_out, const void * weight, size_t nbytes, const float * bias);
+WHISPER_API int whisper_project(struct whisper_context * ctx, float * dst, size_t n_floats);
+WHISPER_API int whisper_projection_dims(struct whisper_context * ctx, int * n_rows, int * n_out);
 /* the underlying C-ABI state handle (q2w_state*, include/q2w_b200.h) for callers that need streams / device pointers */
 WHISPER_API void * whisper_q2w_state(struct whisper_context * ctx);
 

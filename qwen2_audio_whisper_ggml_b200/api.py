@@ -91,6 +91,9 @@ _WSIGS = {
     "whisper_encode_batch_multi": (_i, [_vp, _vp, _sz, _vp, _i, _vp, _i]),
     "whisper_get_gathered_device": (_vp, [_vp]),
     "whisper_q2w_multi": (_vp, [_vp]),
+    "whisper_set_projector": (_i, [_vp, _i, _i, _vp, _sz, _vp]),
+    "whisper_project": (_i, [_vp, _vp, _sz]),
+    "whisper_projection_dims": (_i, [_vp, C.POINTER(_i), C.POINTER(_i)]),
 }
 _bound = False
 
@@ -329,6 +332,25 @@ class Context:
 
     def q2w_state(self) -> int:
         return wlib().whisper_q2w_state(self._h)
+
+    def set_projector(self, weight: np.ndarray, bias: np.ndarray | None = None) -> int:
+        """multi_modal_projector.linear: weight [n_out, n_audio_state] float32 or float16, bias [n_out] float32"""
+        w = np.ascontiguousarray(weight)
+        assert w.dtype in (np.float32, np.float16) and w.ndim == 2
+        b = None if bias is None else _f32(bias)
+        return wlib().whisper_set_projector(self._h, 0 if w.dtype == np.float32 else 1, w.shape[0], w.ctypes.data, w.nbytes,
+                                            None if b is None else b.ctypes.data)
+
+    def project(self) -> np.ndarray:
+        """projector applied to the embeddings of the last encode: [n_windows, n_audio_ctx // 2, n_out]"""
+        nw, no, _ = self.embd_dims()
+        a, b = _i(), _i()
+        if wlib().whisper_projection_dims(self._h, C.byref(a), C.byref(b)) != 0 or b.value <= 0:
+            raise _l.Q2WError(-1, "no projector set")
+        out = np.empty((nw, no, b.value), dtype=np.float32)
+        if wlib().whisper_project(self._h, out.ctypes.data, out.size) != 0:
+            raise _l.Q2WError(-1, "whisper_project failed: " + _l.load_library().q2w_last_error().decode("utf-8", "replace"))
+        return out
 
     def debug_forward_layers(self, n_layers: int) -> None:
         """stage tap (parity tests): every following forward stops after n_layers encoder blocks (-1 = all)"""

@@ -29,7 +29,8 @@ __device__ __forceinline__ float warp_sum(float v) {
 template <bool POOL, typename OutT>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
-                 OutT* __restrict__ y, int rows_out, int D, float eps, int T /*POOL: input rows per window*/) {
+                 OutT* __restrict__ y, int rows_out, int D, float eps, int T /*POOL: input rows per window*/,
+                 __half* __restrict__ y16 /*optional second output in F16 (the projector's A operand), F32-output variant only*/) {
     pdl_wait();               // predecessor grid complete + visible (launch.cuh)
     pdl_launch_dependents();
     const int widx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -99,6 +100,13 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, c
                 reinterpret_cast<uint2*>(y + static_cast<size_t>(warp) * D)[idx] = pk;
             } else {
                 reinterpret_cast<float4*>(y + static_cast<size_t>(warp) * D)[idx] = make_float4(o0, o1, o2, o3);
+                if (y16 != nullptr) {
+                    __half2 h0 = __floats2half2_rn(o0, o1), h1 = __floats2half2_rn(o2, o3);
+                    uint2 pk;
+                    pk.x = *reinterpret_cast<uint32_t*>(&h0);
+                    pk.y = *reinterpret_cast<uint32_t*>(&h1);
+                    reinterpret_cast<uint2*>(y16 + static_cast<size_t>(warp) * D)[idx] = pk;
+                }
             }
         }
     }
@@ -276,16 +284,17 @@ cudaError_t layernorm_f32_to_f16(const float* x, const float* gamma, const float
     if (D % 4 || D > LN_MAX_VPL * 128 || M <= 0) return cudaErrorInvalidValue;
     const int warps_per_block = 8;
     const int grid = (M + warps_per_block - 1) / warps_per_block;
-    return launch_pdl(layernorm_kernel<false, __half>, dim3(grid), dim3(warps_per_block * 32), 0, st, x, gamma, beta, y, M, D, eps, 0);
+    return launch_pdl(layernorm_kernel<false, __half>, dim3(grid), dim3(warps_per_block * 32), 0, st, x, gamma, beta, y, M, D, eps, 0,
+                      static_cast<__half*>(nullptr));
 }
 
 cudaError_t pool2_layernorm_f32(const float* x, const float* gamma, const float* beta, float* y, int B, int T, int D,
-                                float eps, cudaStream_t st) {
+                                float eps, cudaStream_t st, __half* y16) {
     if (D % 4 || D > LN_MAX_VPL * 128 || B <= 0 || T < 2) return cudaErrorInvalidValue;
     const int rows_out = B * (T / 2);
     const int warps_per_block = 8;
     const int grid = (rows_out + warps_per_block - 1) / warps_per_block;
-    return launch_pdl(layernorm_kernel<true, float>, dim3(grid), dim3(warps_per_block * 32), 0, st, x, gamma, beta, y, rows_out, D, eps, T);
+    return launch_pdl(layernorm_kernel<true, float>, dim3(grid), dim3(warps_per_block * 32), 0, st, x, gamma, beta, y, rows_out, D, eps, T, y16);
 }
 
 cudaError_t mel_to_conv1_operand(const float* mel, int ld_frames, int n_frames_valid, int n_mel, const float* win_max,

@@ -99,6 +99,10 @@ struct q2w_model {
     std::vector<Layer> layers;
     std::map<std::string, Tensor*> by_name;
     MelPlan* mel = nullptr;
+    // optional step AFTER the path: Qwen2-Audio's multi_modal_projector, one Linear(n_audio_state -> n_out) with bias
+    __half* proj_w = nullptr;   // [n_out][n_audio_state] f16
+    float* proj_b = nullptr;    // [n_out]
+    int proj_out = 0;
     int n_loaded = 0;
     bool finalized = false;
     size_t weight_bytes = 0;
@@ -144,6 +148,10 @@ struct q2w_state {
     uint64_t mb_seq = 0;            // running micro-batch index: staging slot = mb_seq & 1, across calls
     // results
     float* emb = nullptr;      // [n_windows, T/2, D]
+    __half* emb16 = nullptr;   // the same rows in F16 (only when the model carries a projector: written by the pool + LN tail)
+    float* proj = nullptr;     // [n_windows * T/2, proj_out] f32, q2w_project
+    size_t proj_cap_rows = 0;  // capacity of proj in floats
+    int proj_rows = 0;
     size_t emb_cap_windows = 0;
     int emb_windows = 0;
     // API mel (whisper_pcm_to_mel / whisper_set_mel)
@@ -391,19 +399,27 @@ int forward_eager(q2w_state* s, int Bm, int w0) {
     }
     // avg-pool(2,2) over time + final LayerNorm   (:2160-2181)
     float* out = s->emb + static_cast<size_t>(w0) * (T / 2) * D;
+    __half* out16 = s->emb16 ? s->emb16 + static_cast<size_t>(w0) * (T / 2) * D : nullptr;
     ProfScope ps(s, PC_LN, 0.0, 6.0 * M * D);
     CKL(pool2_layernorm_f32(s->x, static_cast<const float*>(m->ln_w.d), static_cast<const float*>(m->ln_b.d), out, Bm, T, D, eps,
-                            s->stream));
+                            s->stream, out16));
     return Q2W_OK;
 }
 
 int ensure_emb(q2w_state* s, int n_windows) {
-    if (static_cast<size_t>(n_windows) > s->emb_cap_windows) {
+    const bool want16 = s->m->proj_w != nullptr;
+    if (static_cast<size_t>(n_windows) > s->emb_cap_windows || (want16 && !s->emb16)) {
+        const size_t cap = std::max(static_cast<size_t>(n_windows), s->emb_cap_windows);
         if (s->emb) cudaFree(s->emb);
+        if (s->emb16) cudaFree(s->emb16);
         s->emb = nullptr;
+        s->emb16 = nullptr;
         s->emb_cap_windows = 0;
-        CK(cudaMalloc(&s->emb, static_cast<size_t>(n_windows) * (s->T / 2) * s->D * sizeof(float)));
-        s->emb_cap_windows = n_windows;
+        if (s->g1) { cudaGraphExecDestroy(s->g1); s->g1 = nullptr; }     // the captured single-window graph wrote into the old buffers
+        if (s->g1_state == 2) s->g1_state = 1;
+        CK(cudaMalloc(&s->emb, cap * (s->T / 2) * s->D * sizeof(float)));
+        if (want16) CK(cudaMalloc(&s->emb16, cap * (s->T / 2) * s->D * sizeof(__half)));
+        s->emb_cap_windows = cap;
     }
     return Q2W_OK;
 }
@@ -617,11 +633,48 @@ void q2w_model_free(q2w_model* m) {
     free_tensor(m->pe); free_tensor(m->conv1_w); free_tensor(m->conv1_b); free_tensor(m->conv2_w); free_tensor(m->conv2_b);
     free_tensor(m->ln_w); free_tensor(m->ln_b);
     if (m->mel) mel_plan_destroy(m->mel);
+    if (m->proj_w) cudaFree(m->proj_w);
+    if (m->proj_b) cudaFree(m->proj_b);
     if (m->stream) cudaStreamDestroy(m->stream);
     delete m;
 }
 
 int q2w_model_device(const q2w_model* m) { return m ? m->device : -1; }
+
+// The step after the path: Qwen2-Audio's multi_modal_projector = Linear(n_audio_state -> n_out) + bias on every
+// embedding row (HF Qwen2AudioMultiModalProjector.linear). The reference stops at the final LayerNorm (src/qwen2-whisper.cpp:2175-2185);
+// this is additive and optional: a model without it behaves exactly as before.
+int q2w_model_upload_projector(q2w_model* m, int ggml_type, int n_out, const void* w_host, size_t nbytes, const float* bias_host) {
+    if (!m || !w_host) return fail(Q2W_E_INVALID, "null argument");
+    const int D = m->hp.n_audio_state;
+    if (ggml_type != Q2W_TYPE_F32 && ggml_type != Q2W_TYPE_F16) return fail(Q2W_E_UNSUPPORTED, "projector weights must be F32 or F16");
+    if (n_out <= 0 || n_out % 8) return fail(Q2W_E_BAD_SHAPE, "projector width %d must be a positive multiple of 8", n_out);
+    if (nbytes != type_row_bytes(ggml_type, D) * static_cast<size_t>(n_out)) return fail(Q2W_E_BAD_SIZE, "projector weight has %zu bytes, expected [%d][%d]", nbytes, n_out, D);
+    CK(cudaSetDevice(m->device));
+    if (m->proj_w) { cudaFree(m->proj_w); m->proj_w = nullptr; }
+    if (m->proj_b) { cudaFree(m->proj_b); m->proj_b = nullptr; }
+    m->proj_out = 0;
+    CK(cudaMalloc(reinterpret_cast<void**>(&m->proj_w), static_cast<size_t>(n_out) * D * sizeof(__half)));
+    CK(cudaMalloc(reinterpret_cast<void**>(&m->proj_b), static_cast<size_t>(n_out) * sizeof(float)));
+    cudaError_t e;
+    if (ggml_type == Q2W_TYPE_F16) {
+        e = cudaMemcpyAsync(m->proj_w, w_host, nbytes, cudaMemcpyHostToDevice, m->stream);
+    } else {
+        void* tmp = nullptr;
+        CK(cudaMalloc(&tmp, nbytes));
+        e = cudaMemcpyAsync(tmp, w_host, nbytes, cudaMemcpyHostToDevice, m->stream);
+        if (e == cudaSuccess) e = dequant_to_f16(tmp, Q2W_TYPE_F32, m->proj_w, static_cast<size_t>(n_out), D, m->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(m->stream);
+        cudaFree(tmp);
+    }
+    if (e == cudaSuccess) e = bias_host ? cudaMemcpyAsync(m->proj_b, bias_host, sizeof(float) * n_out, cudaMemcpyHostToDevice, m->stream)
+                                        : cudaMemsetAsync(m->proj_b, 0, sizeof(float) * n_out, m->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(m->stream);
+    if (e != cudaSuccess) return fail(Q2W_E_CUDA, "projector upload failed: %s", cudaGetErrorString(e));
+    m->proj_out = n_out;
+    return Q2W_OK;
+}
+int q2w_model_projector_width(const q2w_model* m) { return m ? m->proj_out : 0; }
 int q2w_model_n_tensors_expected(const q2w_model* m) { return m ? static_cast<int>(m->by_name.size()) : 0; }
 int q2w_model_n_tensors_loaded(const q2w_model* m) { return m ? m->n_loaded : 0; }
 size_t q2w_model_weight_bytes(const q2w_model* m) { return m ? m->weight_bytes : 0; }
@@ -747,7 +800,7 @@ void q2w_state_free(q2w_state* s) {
     if (s->s_out) cudaStreamSynchronize(s->s_out);
     free_workspaces(s);
     if (s->s_dq) cudaStreamSynchronize(s->s_dq);
-    void* ptrs[] = {s->wlayer[0], s->wlayer[1], s->emb, s->api_mel, s->api_pcm, s->api_max, s->att_sched};
+    void* ptrs[] = {s->wlayer[0], s->wlayer[1], s->emb, s->emb16, s->proj, s->api_mel, s->api_pcm, s->api_max, s->att_sched};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (int i = 0; i < 2; ++i) {
         if (s->ev_dq[i]) cudaEventDestroy(s->ev_dq[i]);
@@ -897,7 +950,7 @@ static int encode_batch_impl(q2w_state* s, const float* pcm, bool pcm_on_host, s
     if (async_ticket) {
         region = s->next_ticket & 1;
         if (s->ticket_live[region] && (rc = ticket_wait(s, s->next_ticket - 2))) return rc;   // at most two batches in flight
-        if (2 * static_cast<size_t>(B) > s->emb_cap_windows) {                                 // growing the buffer: nothing may be in flight
+        if (2 * static_cast<size_t>(B) > s->emb_cap_windows || (s->m->proj_w && !s->emb16)) {   // (re)allocating: nothing may be in flight
             if ((rc = drain_tickets(s))) return rc;
             if ((rc = ensure_emb(s, 2 * B))) return rc;
         }
@@ -1002,6 +1055,40 @@ int q2w_get_embeddings(q2w_state* s, float* out_host, size_t offset_floats, size
     CK(cudaStreamSynchronize(s->stream));
     return Q2W_OK;
 }
+
+// projector on the embeddings of the last encode / encode_batch: one tcgen05 GEMM, A = the F16 rows the pool + LN tail wrote
+int q2w_project(q2w_state* s, float* out_host, size_t n_floats) {
+    if (!s) return fail(Q2W_E_INVALID, "null argument");
+    q2w_model* m = s->m;
+    if (!m->proj_w || m->proj_out <= 0) return fail(Q2W_E_INVALID, "the model has no projector (q2w_model_upload_projector)");
+    if (!s->emb16 || s->emb_windows <= 0) return fail(Q2W_E_INVALID, "no embeddings to project: encode after the projector was uploaded");
+    CK(cudaSetDevice(m->device));
+    const int rows = s->emb_windows * (s->T / 2);
+    const int N = m->proj_out, D = s->D;
+    if (static_cast<size_t>(rows) * N > s->proj_cap_rows) {          // capacity in floats (the projector width may change between calls)
+        if (s->proj) cudaFree(s->proj);
+        s->proj = nullptr; s->proj_cap_rows = 0;
+        CK(cudaMalloc(reinterpret_cast<void**>(&s->proj), static_cast<size_t>(rows) * N * sizeof(float)));
+        s->proj_cap_rows = static_cast<size_t>(rows) * N;
+    }
+    const __half* A = s->emb16 + s->emb_off_windows * (s->T / 2) * D;
+    int rc = weight_gemm(s, A, D, m->proj_w, Q2W_TYPE_F16, true, rows, N, D, m->proj_b, s->proj, N, EPI_BIAS_F32, nullptr, nullptr, 0, 0, 1.f);
+    if (rc) return rc;
+    s->proj_rows = rows;
+    if (out_host) {
+        if (n_floats < static_cast<size_t>(rows) * N) return fail(Q2W_E_INVALID, "output buffer too small for [%d][%d]", rows, N);
+        CK(cudaMemcpyAsync(out_host, s->proj, static_cast<size_t>(rows) * N * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+    }
+    CK(cudaStreamSynchronize(s->stream));
+    return Q2W_OK;
+}
+int q2w_projection_dims(const q2w_state* s, int* n_rows, int* n_out) {
+    if (!s) return fail(Q2W_E_INVALID, "null argument");
+    if (n_rows) *n_rows = s->proj_rows;
+    if (n_out) *n_out = s->m->proj_out;
+    return Q2W_OK;
+}
+const float* q2w_projected_device(const q2w_state* s) { return s ? s->proj : nullptr; }
 
 const float* q2w_embeddings_device(const q2w_state* s) { return s && s->emb ? s->emb + s->emb_off_windows * (s->T / 2) * s->D : nullptr; }
 

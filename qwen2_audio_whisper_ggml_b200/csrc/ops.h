@@ -46,8 +46,9 @@ void gemm_set_splitk_mode(int mode);
 cudaError_t layernorm_f32_to_f16(const float* x, const float* gamma, const float* beta, __half* y, int M, int D,
                                  float eps, cudaStream_t st);
 // ---- tail: avg-pool(k=2,s=2) over time then LayerNorm, f32 out.  x [B*T, D] -> y [B*(T/2), D]
+// y16 (optional): the same rows rounded to F16 -- the A operand of the multi-modal projector GEMM, written by the same pass
 cudaError_t pool2_layernorm_f32(const float* x, const float* gamma, const float* beta, float* y, int B, int T, int D,
-                                float eps, cudaStream_t st);
+                                float eps, cudaStream_t st, __half* y16 = nullptr);
 
 // ---- attention (non-causal, no mask, Q pre-scaled): qkv f16 [B*T, 3*D] (q | k | v blocks of D = H*64), out f16 [B*T, D]
 // sched: two ints of device memory, zero before the first launch (the kernel leaves them zero again); one buffer per stream

@@ -771,6 +771,29 @@ int whisper_encode_offsets(struct whisper_context* ctx, const int32_t* mel_offse
     }
     return 0;
 }
+// multi-modal projector (additive): uploaded to every replica; whisper_project runs it on the default state's last embeddings
+int whisper_set_projector(struct whisper_context* ctx, int ggml_type, int n_out, const void* weight, size_t nbytes, const float* bias) {
+    if (!ctx) return -1;
+    for (q2w_model* m : ctx->replicas) {
+        if (q2w_model_upload_projector(m, ggml_type, n_out, weight, nbytes, bias) != Q2W_OK) {
+            LOG_ERROR("%s: %s\n", __func__, q2w_last_error());
+            return -1;
+        }
+    }
+    return 0;
+}
+int whisper_project(struct whisper_context* ctx, float* dst, size_t n_floats) {
+    if (!ctx || !ctx->state) return -1;
+    if (q2w_project(ctx->state->qs, dst, n_floats) != Q2W_OK) {
+        LOG_ERROR("%s: %s\n", __func__, q2w_last_error());
+        return -1;
+    }
+    return 0;
+}
+int whisper_projection_dims(struct whisper_context* ctx, int* n_rows, int* n_out) {
+    if (!ctx || !ctx->state) return -1;
+    return q2w_projection_dims(ctx->state->qs, n_rows, n_out) == Q2W_OK ? 0 : -1;
+}
 void* whisper_q2w_state(struct whisper_context* ctx) { return (ctx && ctx->state) ? ctx->state->qs : nullptr; }
 
 }  // extern "C"

@@ -76,6 +76,11 @@ _SIGS = {
     "q2w_debug_forward_layers": (_i, [_vp, _i]),
     "q2w_debug_get_residual": (_i, [_vp, _i, _vp]),
     "q2w_model_device": (_i, [_vp]),
+    "q2w_model_upload_projector": (_i, [_vp, _i, _i, _vp, _sz, _vp]),
+    "q2w_model_projector_width": (_i, [_vp]),
+    "q2w_project": (_i, [_vp, _vp, _sz]),
+    "q2w_projection_dims": (_i, [_vp, C.POINTER(_i), C.POINTER(_i)]),
+    "q2w_projected_device": (_vp, [_vp]),
     "q2w_multi_create": (_i, [C.POINTER(_vp), C.POINTER(_vp), _i, _i]),
     "q2w_multi_free": (None, [_vp]),
     "q2w_multi_n_devices": (_i, [_vp]),

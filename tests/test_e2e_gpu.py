@@ -691,3 +691,38 @@ def test_cli_on_samples_jfk_full_model(tmp_path):
     got = np.array([float(x) for x in lines[0].split()])
     want = np.load(path)["jfk_first20"]
     assert got.shape == (20,) and np.abs(got - want).max() < 5e-3 + TOL["f16"]["max_abs"] / 2, np.abs(got - want).max()
+
+
+def test_multi_modal_projector_after_the_path():
+    """Linear(n_audio_state -> n_out) + bias on every embedding row (HF Qwen2AudioMultiModalProjector.linear) as one more
+    tcgen05 GEMM fed by the F16 rows the pool + final-LayerNorm kernel writes in the same pass; checked against the same Linear in
+    F32 on the library's own embeddings (F16-rounded A and W, F32 accumulate), single window, batch, and a width that is not a tile multiple"""
+    ctx, _ = tiny_ctx("f16", seed=21)
+    D = synth.TINY_HPARAMS["n_audio_state"]
+    rng = np.random.default_rng(9)
+    pcm = synth.synth_pcm(32000, seed=3)
+    assert ctx.full(pcm) == 0
+    before = ctx.get_embeddings()
+    with pytest.raises(Exception):
+        ctx.project()                                               # no projector yet
+    for n_out, dt in ((96, np.float32), (264, np.float16)):
+        W = (rng.standard_normal((n_out, D)) / np.sqrt(D)).astype(dt)
+        b = (0.1 * rng.standard_normal(n_out)).astype(np.float32)
+        assert ctx.set_projector(W, b) == 0
+        assert ctx.full(pcm) == 0
+        emb = ctx.get_embeddings()
+        assert np.array_equal(emb, before)                          # the encoder output itself is unchanged by the extra F16 store
+        got = ctx.project()
+        want = emb[0].astype(np.float16).astype(np.float32) @ W.astype(np.float16).astype(np.float32).T + b
+        assert got.shape == (1, emb.shape[1], n_out) and rel_l2(got[0], want) < 2e-5, rel_l2(got[0], want)
+    win = 2 * synth.TINY_HPARAMS["n_audio_ctx"] * 160
+    batch = np.stack([synth.synth_pcm(win, seed=70 + k, kind="chirp" if k % 2 else "noise") for k in range(5)])
+    ctx.set_max_batch(2)
+    embs = ctx.encode_batch(batch)
+    proj = ctx.project()
+    assert proj.shape == (5, embs.shape[1], 264)
+    for k in range(5):
+        want = embs[k].astype(np.float16).astype(np.float32) @ W.astype(np.float16).astype(np.float32).T + b
+        assert rel_l2(proj[k], want) < 2e-5, k
+    assert ctx.set_projector(np.zeros((100, D), np.float32)) == -1   # width must be a multiple of 8
+    ctx.free()
