@@ -11,6 +11,11 @@ under torchrun (RANK / LOCAL_RANK / WORLD_SIZE); windows are sharded, weights re
   e2e          the same metric through the reference-facing call (whisper_encode_batch) with pinned HOST buffers:
                H2D of the PCM and D2H of the embeddings inside the timed region
   roofline     the dominant kernel (tcgen05 weight GEMM): algorithmic FLOPs / CUDA-event time, measured live in the timed steps
+  parity       what was timed is checked: window 0 of every batch is the golden clip on the golden model; after the B = 1 loop, after the
+               last device-resident step and on the host buffer of the last e2e step its rows are compared with tests/golden/full_<wtype>.npz
+               (the reference's own output); a mismatch exits non-zero
+  configs      the other weight types / BASELINE configurations as short ride-along passes on the same GPUs: Q8_0 and Q4_0 weak passes
+               (64 windows per GPU), Q8_0 / Q4_0 256 windows and F16 120 windows (1 h of audio) in total, sharded over the ranks
   cpu_baseline the UNMODIFIED reference (oracle/_ref, ggml CPU backend) on this box's host cores, one window (rank 0, N = 1)
   --impl reference   times only that reference arm and prints the same line with "impl": "reference"
 """
