@@ -31,6 +31,7 @@
 #include "ops.h"
 #include "launch.cuh"
 #include "ptx.cuh"
+#include "dequant.cuh"
 
 #include <atomic>
 #include <cstdio>
@@ -126,7 +127,8 @@ __device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("ba
 // (a third of a one-item CTA's lifetime, measured) are paid once per CTA instead of once per item.
 __global__ void __launch_bounds__(THREADS, 2)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUtensorMap tm_out, int T, int D, int n_qt, int H, int n_items,
-                    int* __restrict__ sched /* [0] next item, [1] finished CTAs; zero on entry, zero again on exit */) {
+                    int* __restrict__ sched /* [0] next item, [1] finished CTAs; zero on entry, zero again on exit */,
+                    const DequantJob job /* weight matrices to decode meanwhile (warps 2-3), all nblocks 0 = nothing */, int job_type) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sQ = smem;                         // [2]
@@ -294,6 +296,48 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constan
                     umma_commit(pv_done);
                     umma_commit(&v_empty[g & 1]);
                 }
+            }
+        } else if (warp >= 2 && job_type != 0) {
+            // ------------------------------------------------------------ rider: ggml block decode (warps 2 and 3 are otherwise idle)
+            // Quantised weights stay Q8_0 / Q4_0 in HBM; the F16 copy the next GEMMs read is produced HERE, under the attention kernel,
+            // because nothing else can run next to the encoder's kernels at small batch: a GEMM CTA owns its SM's shared memory and TMEM,
+            // two attention CTAs own the register file -- a decode kernel on a second stream only runs in the gaps and delays their CTAs
+            // (measured: single-window p50 4.2 ms against 3.45 ms for an F16 file). These 64 threads per CTA have 56 registers, no
+            // shared memory and nothing to do; they walk the job in pairs of ggml blocks (68 / 36 bytes, 4-byte aligned), one pair per
+            // thread per step, values bit-identical to dequantize_row_* + one F16 rounding (decode_row, dequant.cuh).
+            const unsigned long long tid = static_cast<unsigned long long>(blockIdx.x) * 64 + (threadIdx.x - 64);
+            const unsigned long long nthreads = static_cast<unsigned long long>(gridDim.x) * 64;
+            // (constant indices only: a runtime index into the by-value job would put it on the local-memory stack)
+            const unsigned long long n0 = job.nblocks[0] >> 1, n1 = job.nblocks[1] >> 1, n2 = job.nblocks[2] >> 1, n3 = job.nblocks[3] >> 1;
+            const unsigned long long pairs_total = n0 + n1 + n2 + n3;
+            for (unsigned long long pi = tid; pi < pairs_total; pi += nthreads) {
+                unsigned long long pr = pi;
+                const uint8_t* sbase = job.src[0];
+                __half* dbase = job.dst[0];
+                if (pr >= n0) {
+                    pr -= n0; sbase = job.src[1]; dbase = job.dst[1];
+                    if (pr >= n1) {
+                        pr -= n1; sbase = job.src[2]; dbase = job.dst[2];
+                        if (pr >= n2) { pr -= n2; sbase = job.src[3]; dbase = job.dst[3]; }
+                    }
+                }
+                __half* dst = dbase + pr * 64;
+                uint32_t o[32];
+                if (job_type == WT_Q8_0) {
+                    const uint32_t* src = reinterpret_cast<const uint32_t*>(sbase + pr * 68);
+                    uint32_t w[17];
+#pragma unroll
+                    for (int i = 0; i < 17; ++i) w[i] = __ldg(src + i);
+                    decode_row<WT_Q8_0>(w, o);
+                } else {
+                    const uint32_t* src = reinterpret_cast<const uint32_t*>(sbase + pr * 36);
+                    uint32_t w[9];
+#pragma unroll
+                    for (int i = 0; i < 9; ++i) w[i] = __ldg(src + i);
+                    decode_row<WT_Q4_0>(w, o);
+                }
+#pragma unroll
+                for (int c = 0; c < 8; ++c) reinterpret_cast<uint4*>(dst)[c] = make_uint4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
             }
         }
     } else {
@@ -507,7 +551,8 @@ PFN_encodeTiled get_encode_fn() {
 
 }  // namespace
 
-cudaError_t attention_f16_tcgen05(const __half* qkv, __half* out, int B, int T, int H, int* sched, cudaStream_t st) {
+cudaError_t attention_f16_tcgen05(const __half* qkv, __half* out, int B, int T, int H, int* sched, cudaStream_t st, const DequantJob* job,
+                                  int job_type) {
     if (!sched) return cudaErrorInvalidValue;
     if (B <= 0 || T <= 0 || H <= 0) return cudaErrorInvalidValue;
     const int D = H * HD;
@@ -543,7 +588,15 @@ cudaError_t attention_f16_tcgen05(const __half* qkv, __half* out, int B, int T, 
     if (items > 0x7fffffffLL / ((T + BKV - 1) / BKV)) return cudaErrorInvalidValue;
     const int n_items = static_cast<int>(items);
     const int grid = n_items < 2 * num_sms ? n_items : 2 * num_sms;   // persistent: two CTAs per SM
-    return launch_pdl(attention_tc_kernel, dim3(grid), dim3(THREADS), SMEM_BYTES, st, tm, tm_out, T, D, n_qt, H, n_items, sched);
+    DequantJob j{};
+    int jt = 0;
+    if (job != nullptr && (job_type == WT_Q8_0 || job_type == WT_Q4_0)) {
+        j = *job;
+        jt = job_type;
+        for (int i = 0; i < 4; ++i)
+            if ((j.nblocks[i] & 1) || (reinterpret_cast<uintptr_t>(j.src[i]) & 3) || (reinterpret_cast<uintptr_t>(j.dst[i]) & 15)) return cudaErrorInvalidValue;
+    }
+    return launch_pdl(attention_tc_kernel, dim3(grid), dim3(THREADS), SMEM_BYTES, st, tm, tm_out, T, D, n_qt, H, n_items, sched, j, jt);
 }
 
 }  // namespace q2w

@@ -121,11 +121,9 @@ struct q2w_state {
     __half* qkv = nullptr;     // [B*T, 3D]        (aliases conv2 operand A2)
     __half* att = nullptr;     // [B*T, D]         (aliases conv1 operand A1)
     __half* h = nullptr;       // [B*T, 4D]        (aliases conv1 output h1 [B*T2, D])
-    // quantised weights: one encoder block (QKV | out | fc1 | fc2) decoded to F16 per launch, double-buffered, on a side stream one
-    // block ahead of the compute stream
-    __half* wlayer[2] = {nullptr, nullptr};
-    cudaStream_t s_dq = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_dq[2] = {nullptr, nullptr}, ev_lay[2] = {nullptr, nullptr};
+    // quantised weights: the F16 copy of ONE encoder block (QKV | out | fc1 | fc2, 39 MB), rewritten block after block by the decode
+    // warps that ride inside the attention kernel
+    __half* wlayer = nullptr;
     float* pcm_dev = nullptr;  // [2][B, win_samples]  double-buffered host staging (copy of micro-batch i+1 overlaps compute of i)
     int* nsamp_dev = nullptr;  // [2][B]
     cudaStream_t s_in = nullptr, s_out = nullptr;   // copy-in / copy-out streams of the host-buffer batch path
@@ -136,7 +134,7 @@ struct q2w_state {
     bool att_sched_dirty = false;   // a forward pass failed part-way: re-zero the counter before the next launch
     int dbg_layers = -1;       // q2w_debug_forward_layers: stop after this many encoder blocks (-1 = all); eager launches only
     int dbg_windows = 0;       // windows of the last forward still resident in x
-    int fused_dequant = 0;     // Q2W_FUSED_DEQUANT=1: in-kernel decode (A/B); default: one decode launch per block on the side stream
+    int fused_dequant = 0;     // Q2W_FUSED_DEQUANT=1: decode inside the GEMM (A/B); default: decode warps riding in the attention kernel
     int e2e_split = 2;         // Q2W_E2E_SPLIT: micro-batches a synchronous host batch is cut into
     // asynchronous host batches: at most two in flight; ticket t owns embedding region t & 1 and completion event ev_ticket[t & 1]
     cudaEvent_t ev_ticket[2] = {nullptr, nullptr};
@@ -238,26 +236,22 @@ int weight_gemm(q2w_state* s, const __half* A, int lda, const void* W, int wtype
     return Q2W_OK;
 }
 
-// the four weight matrices of encoder block il, decoded to F16 into layer buffer `buf` by ONE launch on the decode stream
-int decode_layer(q2w_state* s, int il, int buf) {
-    q2w_model* m = s->m;
-    Layer& L = m->layers[il];
+// decode job over the layer buffer: entries (matrix k of block il) -> its slot; k: 0 QKV, 1 out, 2 fc1, 3 fc2
+void add_decode(q2w_state* s, DequantJob& job, int slot, int il, int k) {
+    Layer& L = s->m->layers[il];
     const size_t D = s->D, FF = s->FF;
-    DequantJob job{};
     const void* src[4] = {L.qkv_w, L.o_w.d, L.fc1_w.d, L.fc2_w.d};
     const size_t elems[4] = {3 * D * D, D * D, FF * D, D * FF};
-    size_t off = 0;
-    double in_bytes = 0;
-    for (int i = 0; i < 4; ++i) {
-        job.src[i] = static_cast<const uint8_t*>(src[i]);
-        job.dst[i] = s->wlayer[buf] + off;
-        job.nblocks[i] = elems[i] / 32;
-        off += elems[i];
-        in_bytes += static_cast<double>(elems[i] / 32) * (m->wtype_dev == Q2W_TYPE_Q8_0 ? 34 : 18);
-    }
-    ProfScope ps(s, PC_DEQUANT, 0.0, in_bytes + 2.0 * off, s->s_dq);
-    CKL(dequant_multi_to_f16(job, m->wtype_dev, s->s_dq));
-    return Q2W_OK;
+    const size_t off[4] = {0, 3 * D * D, 4 * D * D, 4 * D * D + FF * D};
+    job.src[slot] = static_cast<const uint8_t*>(src[k]);
+    job.dst[slot] = s->wlayer + off[k];
+    job.nblocks[slot] = elems[k] / 32;
+}
+
+double decode_bytes(const q2w_state* s, const DequantJob& job) {
+    double b = 0;
+    for (int i = 0; i < 4; ++i) b += static_cast<double>(job.nblocks[i]) * ((s->m->wtype_dev == Q2W_TYPE_Q8_0 ? 34 : 18) + 64);
+    return b;
 }
 
 int forward_eager(q2w_state* s, int Bm, int w0);
@@ -331,9 +325,9 @@ int forward_eager(q2w_state* s, int Bm, int w0) {
     const float kq_scale = 1.0f / sqrtf(static_cast<float>(D / H));  // :1985
     const int n_layers = s->dbg_layers >= 0 ? std::min(s->dbg_layers, m->hp.n_audio_layer) : m->hp.n_audio_layer;
     // Quantised weights stay Q8_0 / Q4_0 in HBM exactly as in the model file. Two decode strategies:
-    //   layer   (default) one launch decodes a whole block's four matrices into a 39 MB F16 layer buffer on the decode stream, ONE BLOCK
-    //           AHEAD of the compute stream (two buffers): the GEMMs are the plain TMA-fed F16 kernels, the decode is off the critical
-    //           path at every batch size
+    //   rider   (default) the F16 copy of one encoder block lives in a 39 MB layer buffer and is rewritten block after block by the two
+    //           otherwise idle warps of every attention CTA: while attention(l) runs they decode out / fc1 / fc2 of block l (read right
+    //           after it) and QKV of block l + 1. No extra launches, no second stream; the GEMMs are the plain TMA-fed F16 kernels
     //   fused   (Q2W_FUSED_DEQUANT=1) raw ggml blocks go straight into the GEMM and are decoded by its dequant warpgroup: every W tile
     //           is re-decoded by each M-tile that uses it -- measured 2.7x slower at M = 96000 and 1.7x slower at M = 1500
     const bool quant = m->wtype_dev != Q2W_TYPE_F16;
@@ -341,29 +335,26 @@ int forward_eager(q2w_state* s, int Bm, int w0) {
     const bool by_layer = quant && !fused;
     const size_t w_off[4] = {0, static_cast<size_t>(3) * D * D, static_cast<size_t>(4) * D * D, static_cast<size_t>(4) * D * D + static_cast<size_t>(FF) * D};
     if (by_layer && n_layers > 0) {
-        CK(cudaEventRecord(s->ev_fork, s->stream));          // the decode stream joins this pass (and this capture)
-        CK(cudaStreamWaitEvent(s->s_dq, s->ev_fork, 0));
-        if ((rc = decode_layer(s, 0, 0))) return rc;
-        CK(cudaEventRecord(s->ev_dq[0], s->s_dq));
+        DequantJob job{};                                   // block 0's QKV has no attention kernel before it: one stand-alone launch
+        add_decode(s, job, 0, 0, 0);
+        ProfScope ps(s, PC_DEQUANT, 0.0, decode_bytes(s, job));
+        CKL(dequant_multi_to_f16(job, m->wtype_dev, s->stream));
     }
     for (int il = 0; il < n_layers; ++il) {
         Layer& L = m->layers[il];
         const void* w_qkv = L.qkv_w; const void* w_o = L.o_w.d; const void* w_fc1 = L.fc1_w.d; const void* w_fc2 = L.fc2_w.d;
         int wt = m->wtype_dev;
         bool w_static = true;
+        DequantJob job{};
         if (by_layer) {
-            const int buf = il & 1;
-            if (il + 1 < n_layers) {
-                // buffer buf ^ 1 was last read by block il - 1
-                if (il >= 1) CK(cudaStreamWaitEvent(s->s_dq, s->ev_lay[buf ^ 1], 0));
-                if ((rc = decode_layer(s, il + 1, buf ^ 1))) return rc;
-                CK(cudaEventRecord(s->ev_dq[buf ^ 1], s->s_dq));
-            }
-            CK(cudaStreamWaitEvent(s->stream, s->ev_dq[buf], 0));
-            const __half* base = s->wlayer[buf];
+            add_decode(s, job, 0, il, 1);
+            add_decode(s, job, 1, il, 2);
+            add_decode(s, job, 2, il, 3);
+            if (il + 1 < n_layers) add_decode(s, job, 3, il + 1, 0);
+            const __half* base = s->wlayer;
             w_qkv = base + w_off[0]; w_o = base + w_off[1]; w_fc1 = base + w_off[2]; w_fc2 = base + w_off[3];
             wt = Q2W_TYPE_F16;
-            w_static = false;                                  // written by the decode kernel: never fetch it early
+            w_static = false;                                  // written by a kernel of this stream: never fetch it early
         }
         // pre-LN + fused QKV projection (+bias, Q * KQscale)   (:2019-2055)
         {
@@ -377,7 +368,7 @@ int forward_eager(q2w_state* s, int Bm, int w0) {
         // softmax(Q K^T) V per head   (:2080-2106)
         {
             ProfScope ps(s, PC_ATTN, 4.0 * Bm * static_cast<double>(T) * T * D, 8.0 * M * D);
-            CKL(attention_f16_tcgen05(s->qkv, s->att, Bm, T, H, s->att_sched, s->stream));
+            CKL(attention_f16_tcgen05(s->qkv, s->att, Bm, T, H, s->att_sched, s->stream, by_layer ? &job : nullptr, by_layer ? m->wtype_dev : 0));
         }
         // out-proj + bias + residual   (:2112-2120)
         if ((rc = weight_gemm(s, s->att, D, w_o, wt, w_static, M, D, D, static_cast<const float*>(L.o_b.d), s->x, D,
@@ -395,7 +386,6 @@ int forward_eager(q2w_state* s, int Bm, int w0) {
         if ((rc = weight_gemm(s, s->h, FF, w_fc2, wt, w_static, M, D, FF, static_cast<const float*>(L.fc2_b.d), s->x, D,
                               EPI_BIAS_RESID_F32, s->x, nullptr, 0, 0, 1.f)))
             return rc;
-        if (by_layer) CK(cudaEventRecord(s->ev_lay[il & 1], s->stream));
     }
     // avg-pool(2,2) over time + final LayerNorm   (:2160-2181)
     float* out = s->emb + static_cast<size_t>(w0) * (T / 2) * D;
@@ -731,21 +721,13 @@ int q2w_state_create(q2w_state** out, q2w_model* m, int max_batch) {
     const size_t wlayer_elems = static_cast<size_t>(12) * D * D;     // QKV 3 D^2 + out D^2 + fc1 4 D^2 + fc2 4 D^2
     {   // decode strategy for quantised weights, resolved once per state
         const char* e = getenv("Q2W_FUSED_DEQUANT");
-        s->fused_dequant = e ? atoi(e) : 0;              // 1: decode inside the GEMM; 0 (default): per-block decode on the side stream
+        s->fused_dequant = e ? atoi(e) : 0;              // 1: decode inside the GEMM; 0 (default): decode warps riding in the attention kernel
         const char* sp = getenv("Q2W_E2E_SPLIT");
         s->e2e_split = sp ? std::max(1, atoi(sp)) : 2;
     }
     cudaError_t e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = alloc_workspaces(s, max_batch);
-    if (m->wtype_dev != Q2W_TYPE_F16) {
-        for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
-            e = cudaMalloc(reinterpret_cast<void**>(&s->wlayer[i]), wlayer_elems * sizeof(__half));
-            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_dq[i], cudaEventDisableTiming);
-            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_lay[i], cudaEventDisableTiming);
-        }
-        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming);
-        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->s_dq, cudaStreamNonBlocking);
-    }
+    if (m->wtype_dev != Q2W_TYPE_F16 && e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&s->wlayer), wlayer_elems * sizeof(__half));
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->s_in, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->s_out, cudaStreamNonBlocking);
     for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
@@ -799,15 +781,9 @@ void q2w_state_free(q2w_state* s) {
     if (s->s_in) cudaStreamSynchronize(s->s_in);      // asynchronous batches may still be copying from / into caller memory
     if (s->s_out) cudaStreamSynchronize(s->s_out);
     free_workspaces(s);
-    if (s->s_dq) cudaStreamSynchronize(s->s_dq);
-    void* ptrs[] = {s->wlayer[0], s->wlayer[1], s->emb, s->emb16, s->proj, s->api_mel, s->api_pcm, s->api_max, s->att_sched};
+    void* ptrs[] = {s->wlayer, s->emb, s->emb16, s->proj, s->api_mel, s->api_pcm, s->api_max, s->att_sched};
     for (void* p : ptrs) if (p) cudaFree(p);
-    for (int i = 0; i < 2; ++i) {
-        if (s->ev_dq[i]) cudaEventDestroy(s->ev_dq[i]);
-        if (s->ev_lay[i]) cudaEventDestroy(s->ev_lay[i]);
-    }
-    if (s->ev_fork) cudaEventDestroy(s->ev_fork);
-    if (s->s_dq) cudaStreamDestroy(s->s_dq);
+
     for (auto& r : s->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (int i = 0; i < 2; ++i) {
         if (s->ev_in[i]) cudaEventDestroy(s->ev_in[i]);

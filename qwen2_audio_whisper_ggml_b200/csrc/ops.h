@@ -51,8 +51,17 @@ cudaError_t pool2_layernorm_f32(const float* x, const float* gamma, const float*
                                 float eps, cudaStream_t st, __half* y16 = nullptr);
 
 // ---- attention (non-causal, no mask, Q pre-scaled): qkv f16 [B*T, 3*D] (q | k | v blocks of D = H*64), out f16 [B*T, D]
-// sched: two ints of device memory, zero before the first launch (the kernel leaves them zero again); one buffer per stream
-cudaError_t attention_f16_tcgen05(const __half* qkv, __half* out, int B, int T, int H, int* sched, cudaStream_t st);
+// up to four matrices (one encoder block) in ONE launch: src[i] raw ggml blocks (Q8_0 = 8 / Q4_0 = 2), dst[i] f16, nblocks[i] 32-element blocks
+struct DequantJob {
+    const uint8_t* src[4];
+    __half* dst[4];
+    unsigned long long nblocks[4];
+};
+// sched: two ints of device memory, zero before the first launch (the kernel leaves them zero again); one buffer per stream.
+// job (optional): quantised weight matrices (ggml_type job_type = 8 / 2, an even number of blocks each) that the kernel's two idle
+// warps per CTA decode to F16 while the attention runs -- complete when the kernel is.
+cudaError_t attention_f16_tcgen05(const __half* qkv, __half* out, int B, int T, int H, int* sched, cudaStream_t st,
+                                  const DequantJob* job = nullptr, int job_type = 0);
 
 // ---- mel front-end
 struct MelPlan;  // filterbank + tables resident on device
@@ -75,12 +84,6 @@ cudaError_t conv2_im2col(const __half* h1, __half* A2, int B, int T2, int C, cud
 
 // ---- ggml block decode: Q8_0 / Q4_0 / F32 rows -> f16 [rows, K] (K % 32 == 0)
 cudaError_t dequant_to_f16(const void* src, int ggml_type, __half* dst, size_t rows, int K, cudaStream_t st);
-// up to four matrices (one encoder block) in ONE launch: src[i] raw ggml blocks (Q8_0 = 8 / Q4_0 = 2), dst[i] f16, nblocks[i] 32-element blocks
-struct DequantJob {
-    const uint8_t* src[4];
-    __half* dst[4];
-    unsigned long long nblocks[4];
-};
 cudaError_t dequant_multi_to_f16(const DequantJob& job, int ggml_type, cudaStream_t st);
 
 }  // namespace q2w
