@@ -726,3 +726,21 @@ def test_multi_modal_projector_after_the_path():
         assert rel_l2(proj[k], want) < 2e-5, k
     assert ctx.set_projector(np.zeros((100, D), np.float32)) == -1   # width must be a multiple of 8
     ctx.free()
+
+
+def test_multi_device_error_paths():
+    """a device ordinal that does not exist fails the load (NULL, like any init error); an empty / NULL device list is rejected; freeing a
+    multi-device context twice over is safe"""
+    buf = mfm.to_bytes(synth.synth_model(synth.TINY_HPARAMS, WT["f16"], seed=13))
+    with pytest.raises(Exception):
+        Context.init_from_buffer(buf, devices=[0, 63])
+    with pytest.raises(Exception):
+        Context.init_from_buffer(buf, devices=[])
+    p = api.default_context_params()
+    p.gpu_device = 63
+    with pytest.raises(Exception):
+        Context.init_from_buffer(buf, p)
+    ctx = Context.init_from_buffer(buf, devices=[0, 0])
+    ctx.free()
+    ctx.free()
+    Context.init_from_buffer(buf).free()                       # the library is still usable afterwards
