@@ -87,17 +87,11 @@ class ClockSampler(threading.Thread):
         return dict(sm_mhz=statistics.median(busy), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm), power_w_max=max(power))
 
 
-_WEIGHTS_F32 = {}   # seed-1234 random-init weights, generated once per process and converted to each weight type asked for
-
-
 def build_model_bytes(wtype_name: str, hp=None) -> bytes:
     from qwen2_audio_whisper_ggml_b200 import ggml_quant as gq, modelfile as mfm, synth
     wt = {"f16": gq.GGML_TYPE_F16, "q8_0": gq.GGML_TYPE_Q8_0, "q4_0": gq.GGML_TYPE_Q4_0, "f32": gq.GGML_TYPE_F32}[wtype_name]
-    if hp is not None:
-        return mfm.to_bytes(synth.synth_model(hp, wt, seed=1234))
-    if "w" not in _WEIGHTS_F32:
-        _WEIGHTS_F32["w"] = synth.synth_weights(synth.FULL_HPARAMS, 1234)
-    return mfm.to_bytes(mfm.build_model(synth.FULL_HPARAMS, synth.slaney_mel_filters(synth.FULL_HPARAMS["n_mels"]), _WEIGHTS_F32["w"], wt))
+    # (synth caches the seed-1234 F32 weights: they are drawn once per process and converted to each weight type asked for)
+    return mfm.to_bytes(synth.synth_model(hp or synth.FULL_HPARAMS, wt, seed=1234))
 
 
 def synth_windows(B: int, rank: int) -> np.ndarray:

@@ -63,8 +63,23 @@ def synth_pcm(n: int = 480000, seed: int = 0, kind: str = "chirp") -> np.ndarray
     return (i16.astype(np.float32) / np.float32(32768.0)).astype(np.float32)
 
 
+_WEIGHT_CACHE: dict = {}   # the full-size set takes ~10 s to draw; tests and bench ask for the same (hparams, seed) many times
+
+
 def synth_weights(hp: dict, seed: int = 1234) -> dict:
-    """name -> float32 array (numpy shape): matrices N(0, 1/fan_in), biases / pos-emb N(0, 0.02^2), LN gamma 1 + N(0, 0.02^2)."""
+    """name -> float32 array (numpy shape): matrices N(0, 1/fan_in), biases / pos-emb N(0, 0.02^2), LN gamma 1 + N(0, 0.02^2).
+    The returned arrays are shared between callers (cached): treat them as read-only."""
+    key = (tuple(sorted(hp.items())), seed)
+    if key in _WEIGHT_CACHE:
+        return _WEIGHT_CACHE[key]
+    out = _synth_weights(hp, seed)
+    if len(_WEIGHT_CACHE) >= 2:
+        _WEIGHT_CACHE.pop(next(iter(_WEIGHT_CACHE)))
+    _WEIGHT_CACHE[key] = out
+    return out
+
+
+def _synth_weights(hp: dict, seed: int) -> dict:
     rng = np.random.default_rng(seed)
     out = {}
     for name, ne in mfmod.expected_shapes(hp).items():
