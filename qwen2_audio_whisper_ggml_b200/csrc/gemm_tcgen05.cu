@@ -188,7 +188,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         tmem_relinquish_cta2();
     }
     tc_fence_before();
-    cluster_sync_all();          // barrier inits of both CTAs visible before any remote arrive / multicast
+    // The mbarrier inits were published cluster-wide by fence.mbarrier_init.release.cluster (the initialising thread, above); the TMEM base
+    // address needs CTA-level ordering only. So: a CTA barrier, then an execution-only rendezvous of the pair -- not the release / acquire
+    // cluster barrier, whose MEMBAR.ALL.GPU + ERRBAR drain sits on the critical path whenever this CTA could not start early.
+    __syncthreads();
+    cluster_sync_exec_only();    // both CTAs' barriers exist before any remote arrive / multicast
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     // The weights do not depend on the previous kernel: the W tiles of the first ring pass are requested BEFORE griddepcontrol.wait,
@@ -418,7 +422,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     // every TMEM read of this warp for this tile is done: hand the accumulator back to the leader's MMA warp
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive_cluster(&tempty_bar[acc], 0);
+                    if (lane == 0) mbar_arrive_cluster_cta_release(&tempty_bar[acc], 0);   // TMEM reads are ordered by the tcgen05 fence, not by a memory fence
                 }
                 // ---- bias (+ scale / GELU / positional) in registers; the column index is uniform across the warp
                 if (add_bias) {                                    // warp-uniform
@@ -518,7 +522,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
 
     tc_fence_before();
-    cluster_sync_all();          // no CTA leaves (or frees TMEM) while its peer may still signal it
+    cluster_sync_exec_only();    // no CTA leaves (or frees TMEM) while its peer may still signal it; nothing to publish: relaxed arrive
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc_cta2(tmem_base, TMEM_COLS);

@@ -107,12 +107,28 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// execution-only rendezvous of the cluster (no memory ordering: the arrive is relaxed, so no MEMBAR.ALL.GPU drain): "nobody leaves
+// while a peer may still signal it" at the end of a kernel
+__device__ __forceinline__ void cluster_sync_exec_only() {
+    asm volatile("barrier.cluster.arrive.relaxed.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");
+}
 // arrive on the mbarrier at the same smem offset in CTA `cta` of the cluster
 __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
     asm volatile(
         "{\n\t.reg .b32 ra;\n\t"
         "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
         "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+        ::"r"(smem_u32(bar)), "r"(cta)
+        : "memory");
+}
+// the same arrive with CTA-scope release only: for signals whose payload is ordered by other means (tcgen05.fence::before_thread_sync
+// for TMEM reads). The cluster-scope release above compiles to MEMBAR.ALL.GPU + ERRBAR + CGAERRBAR -- a full drain of the thread's
+// outstanding memory operations (TMA stores included) -- which does not belong on the per-tile path of an epilogue warp.
+__device__ __forceinline__ void mbar_arrive_cluster_cta_release(uint64_t* bar, uint32_t cta) {
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
         ::"r"(smem_u32(bar)), "r"(cta)
         : "memory");
 }
