@@ -525,7 +525,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constan
         tc_fence_after();
         tmem_dealloc(tmem_base, TMEM_COLS);
     }
-    if (threadIdx.x == 0 && atomicAdd(sched + 1, 1) == static_cast<int>(gridDim.x) - 1) {   // last CTA out: every CTA has taken its final id
+    // (when the grid covers every item the work counter is never touched: nothing to count, no atomic round trip in the kernel's tail)
+    if (static_cast<int>(gridDim.x) < n_items && threadIdx.x == 0 &&
+        atomicAdd(sched + 1, 1) == static_cast<int>(gridDim.x) - 1) {   // last CTA out: every CTA has taken its final id
         sched[0] = 0;
         sched[1] = 0;
         __threadfence();
