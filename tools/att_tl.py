@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from qwen2_audio_whisper_ggml_b200 import lib as L
 lib = L.load_library()
-B, H, T = 64, 20, 1500
+B, H, T = (int(sys.argv[1]) if len(sys.argv) > 1 else 64), 20, 1500
 g = torch.Generator(device="cuda").manual_seed(0)
 qkv = (torch.randn(B * T, 3 * H * 64, device="cuda", generator=g) * 0.5).half()
 o = torch.empty(B * T, H * 64, device="cuda", dtype=torch.half)
