@@ -188,6 +188,10 @@ Q2W_API int q2w_op_pool_layernorm(const float* x, const float* gamma, const floa
                                   float eps, void* stream);
 Q2W_API int q2w_op_attention(const void* qkv_f16, void* out_f16, int B, int T, int H, void* stream);
 Q2W_API int q2w_op_dequant(const void* src, int ggml_type, void* dst_f16, size_t rows, int K, void* stream);
+/* n <= 4 quantised matrices (raw ggml blocks, Q2W_TYPE_Q8_0 / Q4_0, an even number of 32-element blocks each) -> f16, either by the
+ * stand-alone kernel or (with_attention != 0) by the idle warps of ONE attention launch over qkv -> att_out, as the engine does per block */
+Q2W_API int q2w_op_dequant_multi(const void* const* src, void* const* dst_f16, const unsigned long long* nblocks, int n, int ggml_type,
+                                 int with_attention, const void* qkv_f16, void* att_out_f16, int B, int T, int H, void* stream);
 Q2W_API int q2w_op_conv2_im2col(const void* h1_f16, void* A2_f16, int B, int T2, int C, void* stream);
 /* window slice [offset, offset + n_ctx2) of B mel-major log-mels (zero past n_frames_valid, :2274-2283), optional clamp/normalise from
  * the per-window ordered-int max keys, conv1 im2col layout: A1 f16 [B * n_ctx2][3 * n_mel], column = ic * 3 + k */

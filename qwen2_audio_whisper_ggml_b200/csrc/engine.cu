@@ -1227,6 +1227,38 @@ int q2w_op_dequant(const void* src, int ggml_type, void* dst, size_t rows, int K
     return Q2W_OK;
 }
 
+// up to four quantised matrices decoded to F16: by the stand-alone kernel (with_attention == 0) or by the idle warps of one attention launch
+// over qkv / out (with_attention != 0) -- the way the engine decodes a block's weights
+int q2w_op_dequant_multi(const void* const* src, void* const* dst_f16, const unsigned long long* nblocks, int n, int ggml_type, int with_attention,
+                         const void* qkv, void* att_out, int B, int T, int H, void* stream) {
+    if (!src || !dst_f16 || !nblocks || n < 1 || n > 4) return fail(Q2W_E_INVALID, "bad argument");
+    DequantJob job{};
+    for (int i = 0; i < n; ++i) {
+        job.src[i] = static_cast<const uint8_t*>(src[i]);
+        job.dst[i] = static_cast<__half*>(dst_f16[i]);
+        job.nblocks[i] = nblocks[i];
+    }
+    if (!with_attention) {
+        CKL(dequant_multi_to_f16(job, ggml_type, static_cast<cudaStream_t>(stream)));
+        return Q2W_OK;
+    }
+    static std::mutex mu;
+    static int* sched[64] = {};
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return fail(Q2W_E_INVALID, "device index out of range");
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        if (!sched[dev]) {
+            CK(cudaMalloc(reinterpret_cast<void**>(&sched[dev]), 2 * sizeof(int)));
+            CK(cudaMemset(sched[dev], 0, 2 * sizeof(int)));
+        }
+    }
+    CKL(attention_f16_tcgen05(static_cast<const __half*>(qkv), static_cast<__half*>(att_out), B, T, H, sched[dev], static_cast<cudaStream_t>(stream), &job,
+                              ggml_type));
+    return Q2W_OK;
+}
+
 int q2w_op_conv2_im2col(const void* h1, void* A2, int B, int T2, int C, void* stream) {
     CKL(conv2_im2col(static_cast<const __half*>(h1), static_cast<__half*>(A2), B, T2, C, static_cast<cudaStream_t>(stream)));
     return Q2W_OK;

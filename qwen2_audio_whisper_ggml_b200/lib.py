@@ -95,6 +95,7 @@ _SIGS = {
     "q2w_state_set_max_batch": (_i, [_vp, _i]),
     "q2w_state_max_batch": (_i, [_vp]),
     "q2w_op_dequant": (_i, [_vp, _i, _vp, _sz, _i, _vp]),
+    "q2w_op_dequant_multi": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp]),
     "q2w_op_conv2_im2col": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "q2w_op_mel": (_i, [_vp, _i, _vp, _sz, _vp, _i, _i, _i, _vp, _i, _vp, _i, _vp]),
 }

@@ -269,6 +269,39 @@ def test_conv1_operand(lib, offset, n_valid, normalise):
     assert torch.equal(A1, want)
 
 
+@pytest.mark.parametrize("ttype", [gq.GGML_TYPE_Q8_0, gq.GGML_TYPE_Q4_0])
+@pytest.mark.parametrize("with_attention,B,T,H", [(0, 0, 0, 0), (1, 1, 1500, 20), (1, 3, 333, 4), (1, 1, 64, 2)])
+def test_dequant_multi_and_attention_rider(lib, ttype, with_attention, B, T, H):
+    """four matrices of different sizes decoded in one go -- by the stand-alone kernel, and by the idle warps of an attention launch (grid
+    of 240 / 36 / 1 CTAs): bit-exact against dequantize_row_* + one F16 rounding, and the attention result itself is untouched"""
+    rng = np.random.default_rng(ttype + T)
+    shapes = [(384, 128), (128, 128), (512, 128), (130, 512)]
+    raws, wants, d_src, d_dst = [], [], [], []
+    for (n, k) in shapes:
+        w = (rng.standard_normal((n, k)) * 0.05).astype(np.float32)
+        raw = gq.quantize(w, ttype).reshape(-1)
+        wants.append(gq.dequantize(raw, ttype, k).astype(np.float16).reshape(n, k))
+        d_src.append(torch.from_numpy(raw.copy()).cuda())
+        d_dst.append(torch.full((n, k), float("nan"), device="cuda", dtype=torch.half))
+    PtrArr = C.c_void_p * 4
+    src = PtrArr(*[t.data_ptr() for t in d_src])
+    dst = PtrArr(*[t.data_ptr() for t in d_dst])
+    nb = (C.c_ulonglong * 4)(*[n * k // 32 for (n, k) in shapes])
+    qkv = out = ref = None
+    if with_attention:
+        g = torch.Generator(device="cuda").manual_seed(1)
+        qkv = (torch.randn(B * T, 3 * 64 * H, device="cuda", generator=g) * 0.5).half()
+        out = torch.full((B * T, 64 * H), float("nan"), device="cuda", dtype=torch.half)
+        ref = torch.empty_like(out)
+        ck(lib.q2w_op_attention(qkv.data_ptr(), ref.data_ptr(), B, T, H, None))
+    ck(lib.q2w_op_dequant_multi(src, dst, nb, 4, ttype, with_attention, qkv.data_ptr() if with_attention else None,
+                                out.data_ptr() if with_attention else None, B, T, H, None))
+    for got, want in zip(d_dst, wants):
+        assert np.array_equal(got.cpu().numpy().view(np.uint16), want.view(np.uint16))
+    if with_attention:
+        assert torch.equal(out, ref)
+
+
 def test_conv2_im2col(lib):
     B, T2, Cc = 2, 200, 128
     g = torch.Generator(device="cuda").manual_seed(9)
