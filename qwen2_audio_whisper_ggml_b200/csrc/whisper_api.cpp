@@ -229,7 +229,7 @@ bool model_load(whisper_model_loader* loader, whisper_context& wctx) {
         int64_t nelements = 1;
         int32_t ne[4] = {1, 1, 1, 1};
         for (int i = 0; i < n_dims; ++i) {
-            if (!read_safe(loader, ne[i]) || ne[i] <= 0 || (nelements *= ne[i]) > (int64_t(1) << 40)) {
+            if (!read_safe(loader, ne[i]) || ne[i] <= 0 || (nelements *= ne[i]) > (int64_t(1) << 31)) {   // the largest real tensor has 6.5 M elements
                 LOG_ERROR("%s: truncated or corrupt tensor record (dims)\n", "whisper_model_load");
                 return false;
             }
