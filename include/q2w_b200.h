@@ -59,6 +59,8 @@ Q2W_API int  q2w_model_upload_filters(q2w_model* m, const float* filters, int n_
  * Validates name / element count / shape / byte size exactly like :1807-1833. ne[] is ggml order (innermost first). */
 Q2W_API int  q2w_model_upload_tensor(q2w_model* m, const char* name, int ggml_type, int n_dims, const int32_t* ne,
                                      const void* data, size_t nbytes);
+/* bytes the file must carry for tensor `name` in the model's weight type (0 = unknown name): validate a record BEFORE reading its payload */
+Q2W_API size_t q2w_model_tensor_bytes(const q2w_model* m, const char* name);
 /* all 7 + 15*L tensors present? (:1861)  Builds the fused QKV weight views. */
 Q2W_API int  q2w_model_finalize(q2w_model* m);
 Q2W_API void q2w_model_free(q2w_model* m);

@@ -596,6 +596,13 @@ int q2w_model_upload_tensor(q2w_model* m, const char* name, int ggml_type, int n
     return Q2W_OK;
 }
 
+// bytes the model file must carry for tensor `name` (0: no such tensor) -- lets a loader reject a corrupt record before it reads it
+size_t q2w_model_tensor_bytes(const q2w_model* m, const char* name) {
+    if (!m || !name) return 0;
+    auto it = m->by_name.find(name);
+    return it == m->by_name.end() ? 0 : it->second->file_bytes();
+}
+
 int q2w_model_finalize(q2w_model* m) {
     if (!m) return fail(Q2W_E_INVALID, "null argument");
     if (m->n_loaded != static_cast<int>(m->by_name.size()))

@@ -245,6 +245,17 @@ bool model_load(whisper_model_loader* loader, whisper_context& wctx) {
             return false;
         }
         const size_t nbytes = static_cast<size_t>(nelements) / blck_size(ttype) * bpe;
+        {   // reject a record the model cannot hold before reading (or allocating for) its payload: same messages as :1807 / :1829
+            const size_t want = q2w_model_tensor_bytes(wctx.model, name.c_str());
+            if (want == 0) {
+                LOG_ERROR("%s: unknown tensor '%s' in model file\n", "whisper_model_load", name.c_str());
+                return false;
+            }
+            if (want != nbytes) {
+                LOG_ERROR("%s: tensor '%s' has wrong size in model file: got %zu, expected %zu\n", "whisper_model_load", name.c_str(), nbytes, want);
+                return false;
+            }
+        }
         read_buf.resize(nbytes);
         if (!read_exact(read_buf.data(), nbytes)) {
             LOG_ERROR("%s: truncated model file: tensor '%s' needs %zu bytes\n", "whisper_model_load", name.c_str(), nbytes);

@@ -34,6 +34,7 @@ _SIGS = {
     "q2w_model_create": (_i, [C.POINTER(_vp), C.POINTER(HParams), _i, _i]),
     "q2w_model_upload_filters": (_i, [_vp, _vp, _i, _i]),
     "q2w_model_upload_tensor": (_i, [_vp, C.c_char_p, _i, _i, C.POINTER(C.c_int32), _vp, _sz]),
+    "q2w_model_tensor_bytes": (_sz, [_vp, C.c_char_p]),
     "q2w_model_finalize": (_i, [_vp]),
     "q2w_model_free": (None, [_vp]),
     "q2w_model_n_tensors_expected": (_i, [_vp]),
