@@ -160,6 +160,11 @@ Q2W_API int  q2w_multi_shard_bounds(const q2w_multi* mm, int B, int i, int* lo, 
 Q2W_API int  q2w_multi_set_max_batch(q2w_multi* mm, int max_batch_per_device);
 Q2W_API int  q2w_multi_encode_batch_host(q2w_multi* mm, const float* pcm_host, size_t stride, const int32_t* n_samples, int B,
                                          float* out_host, int gather_device /* -1: no gather */);
+/* asynchronous form (no gather): every device queues its shard and the call returns a ticket; at most two batches in flight, a third
+ * submit first waits for the oldest; pcm_host / out_host must stay valid until q2w_multi_encode_batch_wait(ticket) */
+Q2W_API int  q2w_multi_encode_batch_host_async(q2w_multi* mm, const float* pcm_host, size_t stride, const int32_t* n_samples, int B,
+                                               float* out_host, int* ticket);
+Q2W_API int  q2w_multi_encode_batch_wait(q2w_multi* mm, int ticket);
 Q2W_API const float* q2w_multi_gathered_device(const q2w_multi* mm);
 Q2W_API int  q2w_multi_get_gathered(q2w_multi* mm, float* out_host, size_t n_floats);
 Q2W_API double q2w_multi_last_device_ms(const q2w_multi* mm, int i);   /* device time of replica i's last shard (CUDA events) */

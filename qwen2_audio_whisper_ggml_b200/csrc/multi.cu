@@ -30,6 +30,8 @@ struct Job {
     float* out_host = nullptr;
     int gather_slot = -1;      // index into q2w_multi::workers of the gather target, -1: none
     float* gather_buf = nullptr;
+    int mode = 0;              // 0: synchronous batch; 1: queue the shard (asynchronous host batch); 2: wait for the shard queued under `slot`
+    int slot = 0;              // asynchronous batches: which of the two in-flight batches
 };
 
 struct Worker {
@@ -45,6 +47,7 @@ struct Worker {
     int rc = Q2W_OK;
     std::string err;
     double ms = 0.0;           // device time of the last shard (CUDA events on the worker's stream)
+    int shard_ticket[2] = {-1, -1};   // the state-level tickets of the two asynchronous batches that may be in flight (-1: empty shard)
 };
 
 }  // namespace
@@ -60,6 +63,8 @@ struct q2w_multi {
     int gather_slot = -1;
     int last_B = 0;
     bool peer_enabled = false;
+    int next_ticket = 0;               // asynchronous batches: ticket t lives in slot t & 1
+    bool slot_live[2] = {false, false};
 };
 
 namespace {
@@ -77,10 +82,25 @@ void run_job(q2w_multi* mm, Worker& w) {
     w.rc = Q2W_OK;
     w.err.clear();
     w.ms = 0.0;
-    if (w.hi <= w.lo) return;                                // empty shard (B < number of devices)
     const size_t opw = static_cast<size_t>(mm->n_out) * mm->n_state;
     const int n = w.hi - w.lo;
     cudaSetDevice(w.device);
+    if (j.mode == 1) {                                       // queue this shard and return: copies and kernels overlap across batches
+        w.shard_ticket[j.slot] = -1;
+        if (n <= 0) return;
+        w.rc = q2w_encode_batch_host_async(w.state, j.pcm + static_cast<size_t>(w.lo) * j.stride, j.stride, j.n_samples ? j.n_samples + w.lo : nullptr, n,
+                                           j.out_host + static_cast<size_t>(w.lo) * opw, &w.shard_ticket[j.slot]);
+        if (w.rc != Q2W_OK) w.err = q2w_last_error();
+        return;
+    }
+    if (j.mode == 2) {
+        if (w.shard_ticket[j.slot] < 0) return;
+        w.rc = q2w_encode_batch_wait(w.state, w.shard_ticket[j.slot]);
+        if (w.rc != Q2W_OK) w.err = q2w_last_error();
+        w.shard_ticket[j.slot] = -1;
+        return;
+    }
+    if (n <= 0) return;                                      // empty shard (B < number of devices)
     cudaStream_t st = static_cast<cudaStream_t>(q2w_state_stream(w.state));
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     cudaEventCreate(&e0);
@@ -128,6 +148,33 @@ void worker_main(q2w_multi* mm, int idx) {
         }
         mm->cv_done.notify_all();
     }
+}
+
+// hands every worker its job and waits until all have reported (the workers run concurrently, one per device)
+int dispatch(q2w_multi* mm, const Job& proto, int B) {
+    const int G = static_cast<int>(mm->workers.size());
+    {
+        std::lock_guard<std::mutex> lk(mm->mu);
+        for (int i = 0; i < G; ++i) {
+            Worker& w = mm->workers[i];
+            w.job = proto;
+            if (proto.mode != 2) shard_bounds(B, i, G, w.lo, w.hi);
+            w.done = false;
+            w.has_job = true;
+        }
+    }
+    mm->cv_job.notify_all();
+    {
+        std::unique_lock<std::mutex> lk(mm->mu);
+        mm->cv_done.wait(lk, [&] {
+            for (auto& w : mm->workers)
+                if (!w.done) return false;
+            return true;
+        });
+    }
+    for (auto& w : mm->workers)
+        if (w.rc != Q2W_OK) return q2w::set_last_error(w.rc, (std::string("device ") + std::to_string(w.device) + ": " + w.err).c_str());
+    return Q2W_OK;
 }
 
 }  // namespace
@@ -232,31 +279,49 @@ int q2w_multi_encode_batch_host(q2w_multi* mm, const float* pcm_host, size_t str
             mm->gather_cap_windows = B;
         }
     }
-    {
-        std::lock_guard<std::mutex> lk(mm->mu);
-        for (int i = 0; i < G; ++i) {
-            Worker& w = mm->workers[i];
-            w.job.pcm = pcm_host; w.job.stride = stride; w.job.n_samples = n_samples; w.job.B = B; w.job.out_host = out_host;
-            w.job.gather_slot = gslot;
-            w.job.gather_buf = gslot >= 0 ? mm->gather_buf : nullptr;
-            shard_bounds(B, i, G, w.lo, w.hi);
-            w.done = false;
-            w.has_job = true;
+    for (int t = mm->next_ticket - 2; t < mm->next_ticket; ++t)          // a synchronous call first retires whatever is still in flight
+        if (t >= 0 && mm->slot_live[t & 1]) {
+            const int rc = q2w_multi_encode_batch_wait(mm, t);
+            if (rc != Q2W_OK) return rc;
         }
-    }
-    mm->cv_job.notify_all();
-    {
-        std::unique_lock<std::mutex> lk(mm->mu);
-        mm->cv_done.wait(lk, [&] {
-            for (auto& w : mm->workers)
-                if (!w.done) return false;
-            return true;
-        });
-    }
+    Job j;
+    j.pcm = pcm_host; j.stride = stride; j.n_samples = n_samples; j.B = B; j.out_host = out_host;
+    j.gather_slot = gslot;
+    j.gather_buf = gslot >= 0 ? mm->gather_buf : nullptr;
+    const int rc = dispatch(mm, j, B);
     mm->last_B = B;
-    for (auto& w : mm->workers)
-        if (w.rc != Q2W_OK) return q2w::set_last_error(w.rc, (std::string("device ") + std::to_string(w.device) + ": " + w.err).c_str());
+    return rc;
+}
+
+// Asynchronous form: every device queues its shard (H2D, kernels, D2H on its own streams) and the call returns; at most two batches are
+// in flight (a third submit first waits for the oldest). pcm_host / out_host must stay valid until q2w_multi_encode_batch_wait(ticket).
+int q2w_multi_encode_batch_host_async(q2w_multi* mm, const float* pcm_host, size_t stride, const int32_t* n_samples, int B, float* out_host, int* ticket) {
+    if (!mm || !pcm_host || !out_host || !ticket || B <= 0 || stride == 0) return q2w::set_last_error(Q2W_E_INVALID, "q2w_multi_encode_batch_host_async: bad argument");
+    const int slot = mm->next_ticket & 1;
+    if (mm->slot_live[slot]) {
+        const int rc = q2w_multi_encode_batch_wait(mm, mm->next_ticket - 2);
+        if (rc != Q2W_OK) return rc;
+    }
+    Job j;
+    j.pcm = pcm_host; j.stride = stride; j.n_samples = n_samples; j.B = B; j.out_host = out_host; j.mode = 1; j.slot = slot;
+    const int rc = dispatch(mm, j, B);
+    if (rc != Q2W_OK) return rc;
+    mm->slot_live[slot] = true;
+    mm->last_B = B;
+    *ticket = mm->next_ticket++;
     return Q2W_OK;
+}
+
+int q2w_multi_encode_batch_wait(q2w_multi* mm, int ticket) {
+    if (!mm) return q2w::set_last_error(Q2W_E_INVALID, "null argument");
+    const int slot = ticket & 1;
+    if (ticket < 0 || ticket >= mm->next_ticket || mm->next_ticket - ticket > 2 || !mm->slot_live[slot])
+        return q2w::set_last_error(Q2W_E_INVALID, "ticket is not in flight");
+    Job j;
+    j.mode = 2; j.slot = slot;
+    const int rc = dispatch(mm, j, 0);
+    mm->slot_live[slot] = false;
+    return rc;
 }
 
 const float* q2w_multi_gathered_device(const q2w_multi* mm) { return mm ? mm->gather_buf : nullptr; }

@@ -752,6 +752,13 @@ int whisper_encode_batch(struct whisper_context* ctx, const float* samples, size
 int whisper_encode_batch_async(struct whisper_context* ctx, const float* samples, size_t stride, const int32_t* n_samples, int n_windows, float* dst) {
     if (!ctx || !ctx->state) return -1;
     int ticket = -1;
+    if (ctx->multi) {   // every device queues its shard
+        if (q2w_multi_encode_batch_host_async(ctx->multi, samples, stride, n_samples, n_windows, dst, &ticket) != Q2W_OK) {
+            LOG_ERROR("%s: failed to queue the batch: %s\n", __func__, q2w_last_error());
+            return -1;
+        }
+        return ticket;
+    }
     if (q2w_encode_batch_host_async(ctx->state->qs, samples, stride, n_samples, n_windows, dst, &ticket) != Q2W_OK) {
         LOG_ERROR("%s: failed to queue the batch: %s\n", __func__, q2w_last_error());
         return -1;
@@ -760,6 +767,13 @@ int whisper_encode_batch_async(struct whisper_context* ctx, const float* samples
 }
 int whisper_encode_batch_wait(struct whisper_context* ctx, int ticket) {
     if (!ctx || !ctx->state) return -1;
+    if (ctx->multi) {
+        if (q2w_multi_encode_batch_wait(ctx->multi, ticket) != Q2W_OK) {
+            LOG_ERROR("%s: %s\n", __func__, q2w_last_error());
+            return -1;
+        }
+        return 0;
+    }
     if (q2w_encode_batch_wait(ctx->state->qs, ticket) != Q2W_OK) {
         LOG_ERROR("%s: %s\n", __func__, q2w_last_error());
         return -1;

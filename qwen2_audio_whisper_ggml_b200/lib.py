@@ -90,6 +90,8 @@ _SIGS = {
     "q2w_multi_shard_bounds": (_i, [_vp, _i, _i, C.POINTER(_i), C.POINTER(_i)]),
     "q2w_multi_set_max_batch": (_i, [_vp, _i]),
     "q2w_multi_encode_batch_host": (_i, [_vp, _vp, _sz, _vp, _i, _vp, _i]),
+    "q2w_multi_encode_batch_host_async": (_i, [_vp, _vp, _sz, _vp, _i, _vp, _vp]),
+    "q2w_multi_encode_batch_wait": (_i, [_vp, _i]),
     "q2w_multi_gathered_device": (_vp, [_vp]),
     "q2w_multi_get_gathered": (_i, [_vp, _vp, _sz]),
     "q2w_multi_last_device_ms": (C.c_double, [_vp, _i]),

@@ -517,6 +517,22 @@ def _multi_case(devices):
         assert np.array_equal(out2, want)
         assert np.array_equal(multi.gathered(B), want)         # gathered on device k, ordered by window index
         assert multi.gathered_device_ptr()
+    # asynchronous batches over all replicas: two in flight, a third submit retires the oldest; same bits as the synchronous call
+    import torch as _t
+    ins = [_t.from_numpy(pcm).pin_memory() for _ in range(3)]
+    outs = [_t.full((B,) + want.shape[1:], float("nan")).pin_memory() for _ in range(3)]
+    tk = [multi.encode_batch_async(ins[k].numpy(), outs[k].numpy(), ns) for k in range(3)]
+    assert tk == [0, 1, 2]
+    with pytest.raises(Exception):
+        multi.wait(tk[0])                                      # already retired by the third submit
+    multi.wait(tk[1])
+    multi.wait(tk[2])
+    for k in range(3):
+        assert np.array_equal(outs[k].numpy(), want), k
+    t3 = multi.encode_batch_async(ins[0].numpy(), outs[0].numpy(), ns)
+    assert np.array_equal(multi.encode_batch(pcm, ns), want)   # a synchronous call drains what is in flight
+    with pytest.raises(Exception):
+        multi.wait(t3)
     small = multi.encode_batch_multi(pcm[:1], ns[:1], gather_device=devices[-1])   # fewer windows than replicas: empty shards
     assert np.array_equal(small, want[:1]) and np.array_equal(multi.gathered(1), want[:1])
     # the single-window API keeps working on replica 0

@@ -35,6 +35,21 @@ for name, gather in (("no_gather", -1), ("gather_to_device_0", 0)):
     mm = api.wlib().whisper_q2w_multi(ctx._h)
     dev_ms = [lib.q2w_multi_last_device_ms(mm, i) for i in range(G)] if mm else []
     res[name] = {"audio_s_per_s": 30.0 * B / dt, "ms_per_call": 1e3 * dt, "per_device_ms_last_call": [round(x, 1) for x in dev_ms]}
+out2 = torch.empty_like(out).pin_memory()
+outs = [out, out2]
+def run_async(n):
+    prev = None
+    for i in range(n):
+        t = ctx.encode_batch_async(host.numpy(), outs[i & 1].numpy())
+        if prev is not None:
+            ctx.wait(prev)
+        prev = t
+    ctx.wait(prev)
+run_async(2)
+t0 = time.perf_counter()
+run_async(steps)
+dt = (time.perf_counter() - t0) / steps
+res["async_two_in_flight"] = {"audio_s_per_s": 30.0 * B / dt, "ms_per_call": 1e3 * dt}
 chk = bench.golden_check(out[0].numpy(), wtype)
 res["parity_window0"] = {k: chk[k] for k in ("rel_l2", "max_abs", "ok")} if chk.get("checked") else chk
 same = all(torch.equal(out[g * per_gpu:(g + 1) * per_gpu], out[:per_gpu]) for g in range(1, G))
