@@ -23,7 +23,7 @@
 //               it only bounds the magnitude of P (<= 256 in F16), and the final division by the row sum uses the same reference point.
 //               Item epilogue (O / l -> F16) is deferred into the next item's first tile, staged 128B-swizzled in the finished item's
 //               own Q buffer and written by ONE TMA store (rows >= T clipped by the TMA unit).
-// Registers are rebalanced with setmaxnreg (producer/MMA warpgroup 56, softmax warpgroup 200).
+// Registers are rebalanced with setmaxnreg (producer / MMA / rider-decode warpgroup 72, softmax warpgroup 184).
 // Measured (tools/ubench/xu_pipe.cu, tools/att_clk.py, make EXTRA_NVFLAGS=-DQ2W_ATT_TIMELINE): MUFU.EX2 issues at 8 clk per warp per
 // scheduler and the whole softmax instruction mix fits under it (64.6 clk per 8 elements with two warps per scheduler); the steady
 // state is ~2200 clk per tile per CTA against the 2048-clk MUFU floor of two co-resident CTAs; run back to back the kernel sits at the
@@ -206,7 +206,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constan
     };
 
     if (warp < 4) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
         if (warp == 0 && lane == 0) {
             // ------------------------------------------------------------ TMA producer
             // take the next item, wait until the Q buffer (and id slot) of item it - 2 is really retired, publish, start the Q load
@@ -302,7 +302,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constan
             // Quantised weights stay Q8_0 / Q4_0 in HBM; the F16 copy the next GEMMs read is produced HERE, under the attention kernel,
             // because nothing else can run next to the encoder's kernels at small batch: a GEMM CTA owns its SM's shared memory and TMEM,
             // two attention CTAs own the register file -- a decode kernel on a second stream only runs in the gaps and delays their CTAs
-            // (measured: single-window p50 4.2 ms against 3.45 ms for an F16 file). These 64 threads per CTA have 56 registers, no
+            // (measured: single-window p50 4.2 ms against 3.45 ms for an F16 file). These 64 threads per CTA have 72 registers, no
             // shared memory and nothing to do; they walk the job in pairs of ggml blocks (68 / 36 bytes, 4-byte aligned), one pair per
             // thread per step, values bit-identical to dequantize_row_* + one F16 rounding (decode_row, dequant.cuh).
             const unsigned long long tid = static_cast<unsigned long long>(blockIdx.x) * 64 + (threadIdx.x - 64);
@@ -341,7 +341,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constan
             }
         }
     } else {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 184;");
         // ------------------------------------------------------------ softmax (thread = query row)
         const int qd = warp & 3;
         const int row = qd * 32 + lane;
