@@ -310,34 +310,69 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constan
             // (constant indices only: a runtime index into the by-value job would put it on the local-memory stack)
             const unsigned long long n0 = job.nblocks[0] >> 1, n1 = job.nblocks[1] >> 1, n2 = job.nblocks[2] >> 1, n3 = job.nblocks[3] >> 1;
             const unsigned long long pairs_total = n0 + n1 + n2 + n3;
-            for (unsigned long long pi = tid; pi < pairs_total; pi += nthreads) {
-                unsigned long long pr = pi;
-                const uint8_t* sbase = job.src[0];
-                __half* dbase = job.dst[0];
+            // software-pipelined: the words of pair i + 1 are requested before pair i is decoded (these warps are latency-bound)
+            auto locate = [&](unsigned long long pi, const uint8_t*& sb, __half*& db, unsigned long long& pr) {
+                pr = pi; sb = job.src[0]; db = job.dst[0];
                 if (pr >= n0) {
-                    pr -= n0; sbase = job.src[1]; dbase = job.dst[1];
+                    pr -= n0; sb = job.src[1]; db = job.dst[1];
                     if (pr >= n1) {
-                        pr -= n1; sbase = job.src[2]; dbase = job.dst[2];
-                        if (pr >= n2) { pr -= n2; sbase = job.src[3]; dbase = job.dst[3]; }
+                        pr -= n1; sb = job.src[2]; db = job.dst[2];
+                        if (pr >= n2) { pr -= n2; sb = job.src[3]; db = job.dst[3]; }
                     }
                 }
-                __half* dst = dbase + pr * 64;
-                uint32_t o[32];
-                if (job_type == WT_Q8_0) {
-                    const uint32_t* src = reinterpret_cast<const uint32_t*>(sbase + pr * 68);
-                    uint32_t w[17];
+            };
+            if (job_type == WT_Q8_0) {
+                uint32_t cur[17], nxt[17];
+                const uint8_t* sb; __half* db; unsigned long long pr;
+                unsigned long long pi = tid;
+                if (pi < pairs_total) {
+                    locate(pi, sb, db, pr);
+                    const uint32_t* src = reinterpret_cast<const uint32_t*>(sb + pr * 68);
 #pragma unroll
-                    for (int i = 0; i < 17; ++i) w[i] = __ldg(src + i);
-                    decode_row<WT_Q8_0>(w, o);
-                } else {
-                    const uint32_t* src = reinterpret_cast<const uint32_t*>(sbase + pr * 36);
-                    uint32_t w[9];
-#pragma unroll
-                    for (int i = 0; i < 9; ++i) w[i] = __ldg(src + i);
-                    decode_row<WT_Q4_0>(w, o);
+                    for (int i = 0; i < 17; ++i) cur[i] = __ldg(src + i);
                 }
+                for (; pi < pairs_total; pi += nthreads) {
+                    __half* dst = db + pr * 64;
+                    const unsigned long long pn = pi + nthreads;
+                    if (pn < pairs_total) {
+                        locate(pn, sb, db, pr);
+                        const uint32_t* src = reinterpret_cast<const uint32_t*>(sb + pr * 68);
 #pragma unroll
-                for (int c = 0; c < 8; ++c) reinterpret_cast<uint4*>(dst)[c] = make_uint4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
+                        for (int i = 0; i < 17; ++i) nxt[i] = __ldg(src + i);
+                    }
+                    uint32_t o[32];
+                    decode_row<WT_Q8_0>(cur, o);
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) reinterpret_cast<uint4*>(dst)[c] = make_uint4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
+#pragma unroll
+                    for (int i = 0; i < 17; ++i) cur[i] = nxt[i];
+                }
+            } else {
+                uint32_t cur[9], nxt[9];
+                const uint8_t* sb; __half* db; unsigned long long pr;
+                unsigned long long pi = tid;
+                if (pi < pairs_total) {
+                    locate(pi, sb, db, pr);
+                    const uint32_t* src = reinterpret_cast<const uint32_t*>(sb + pr * 36);
+#pragma unroll
+                    for (int i = 0; i < 9; ++i) cur[i] = __ldg(src + i);
+                }
+                for (; pi < pairs_total; pi += nthreads) {
+                    __half* dst = db + pr * 64;
+                    const unsigned long long pn = pi + nthreads;
+                    if (pn < pairs_total) {
+                        locate(pn, sb, db, pr);
+                        const uint32_t* src = reinterpret_cast<const uint32_t*>(sb + pr * 36);
+#pragma unroll
+                        for (int i = 0; i < 9; ++i) nxt[i] = __ldg(src + i);
+                    }
+                    uint32_t o[32];
+                    decode_row<WT_Q4_0>(cur, o);
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) reinterpret_cast<uint4*>(dst)[c] = make_uint4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
+#pragma unroll
+                    for (int i = 0; i < 9; ++i) cur[i] = nxt[i];
+                }
             }
         }
     } else {
