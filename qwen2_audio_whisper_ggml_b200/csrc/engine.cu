@@ -440,11 +440,12 @@ int drain_tickets(q2w_state* s) {
 }
 
 // mel + conv1 operand for Bm windows resident in s->pcm_dev, then the encoder
-int batch_chunk(q2w_state* s, const float* pcm_dev, size_t stride, const int* nsamp_dev, int Bm, int w0) {
+// nsamp_dev == nullptr: every window of the chunk has n_max valid samples (no per-window length array needed on the device)
+int batch_chunk(q2w_state* s, const float* pcm_dev, size_t stride, const int* nsamp_dev, int n_max, int Bm, int w0) {
     {
         // algorithmic bytes: PCM in + used mel frames out (4*480000 + 4*128*3000 per window)
         ProfScope ps(s, PC_MEL, 0.0, static_cast<double>(Bm) * (4.0 * s->win_samples + 4.0 * s->n_mel * s->T2));
-        CKL(mel_logpower(s->m->mel, pcm_dev, stride, nsamp_dev, s->win_samples, Bm, s->n_frames_batch, s->logmel, s->ld_mel,
+        CKL(mel_logpower(s->m->mel, pcm_dev, stride, nsamp_dev, n_max, Bm, s->n_frames_batch, s->logmel, s->ld_mel,
                          s->winmax, s->stream));
         g_launches.fetch_add(1);  // mel_logpower issues two kernels (key init + main)
     }
@@ -960,12 +961,17 @@ static int encode_batch_impl(q2w_state* s, const float* pcm, bool pcm_on_host, s
         const int Bm = std::min(mb, B - w0);
         const int slot = static_cast<int>(s->mb_seq & 1);
         int* nsamp = s->nsamp_dev + static_cast<size_t>(slot) * s->max_batch;
+        // windows of equal length (the common case: full windows) need no length array on the device -- and a single-window call
+        // then has no host-to-device copy at all in front of its first kernel
+        bool uniform = true;
+        for (int b = 1; b < Bm; ++b) uniform = uniform && ns[w0 + b] == ns[w0];
+        const int n_max = uniform ? ns[w0] : s->win_samples;
         const float* pcm_dev = nullptr;
         size_t dev_stride = stride;
         if (pcm_on_host) {
             float* stage = s->pcm_dev + static_cast<size_t>(slot) * s->max_batch * s->win_samples;
             if (s->mb_seq >= 2) CK(cudaStreamWaitEvent(s->s_in, s->ev_done[slot], 0));   // compute of micro-batch mb_seq - 2 has consumed this slot
-            CK(cudaMemcpyAsync(nsamp, ns.data() + w0, sizeof(int) * Bm, cudaMemcpyHostToDevice, s->s_in));
+            if (!uniform) CK(cudaMemcpyAsync(nsamp, ns.data() + w0, sizeof(int) * Bm, cudaMemcpyHostToDevice, s->s_in));
             CK(cudaMemcpy2DAsync(stage, static_cast<size_t>(s->win_samples) * sizeof(float), pcm + static_cast<size_t>(w0) * stride,
                                  stride * sizeof(float), width * sizeof(float), Bm, cudaMemcpyHostToDevice, s->s_in));
             CK(cudaEventRecord(s->ev_in[slot], s->s_in));
@@ -974,10 +980,10 @@ static int encode_batch_impl(q2w_state* s, const float* pcm, bool pcm_on_host, s
             dev_stride = s->win_samples;
         } else {
             if (s->mb_seq >= 2) CK(cudaStreamWaitEvent(s->stream, s->ev_done[slot], 0));
-            CK(cudaMemcpyAsync(nsamp, ns.data() + w0, sizeof(int) * Bm, cudaMemcpyHostToDevice, s->stream));
+            if (!uniform) CK(cudaMemcpyAsync(nsamp, ns.data() + w0, sizeof(int) * Bm, cudaMemcpyHostToDevice, s->stream));
             pcm_dev = pcm + static_cast<size_t>(w0) * stride;
         }
-        if ((rc = batch_chunk(s, pcm_dev, dev_stride, nsamp, Bm, static_cast<int>(emb_base) + w0))) return rc;
+        if ((rc = batch_chunk(s, pcm_dev, dev_stride, uniform ? nullptr : nsamp, n_max, Bm, static_cast<int>(emb_base) + w0))) return rc;
         CK(cudaEventRecord(s->ev_done[slot], s->stream));
         if (out_host) {
             CK(cudaStreamWaitEvent(s->s_out, s->ev_done[slot], 0));
